@@ -1,0 +1,438 @@
+// k1_decode.cu -- K1: GSLIB ASCII grid decoder (text -> float32), and its inverse
+//
+// Replaces the reference's per-line `grid.readline()` + `float()`
+// (GSIMCLI/tools/grid.py:673, 820-823; tools/utils.py:66-78) and
+// np.loadtxt(skiprows) (grid.py:326).  One number per line, Python float()
+// syntax.  Conversion is decimal -> float64 correctly rounded (what float()
+// returns) -> float32 round-to-nearest-even (our storage cast):
+//   * <= 15 significant digits and |e10| <= 22: Clinger's fast path, one exact
+//     u64->f64 conversion and one correctly rounded multiply/divide;
+//   * up to 19 digits, -21 <= e10 <= 27: exact 128-bit integer arithmetic with
+//     round-half-even;
+//   * anything else: GSB_EPARSE (never a host fallback).
+// Two line-addressing modes:
+//   * fixed-width records (line_width > 0): O(1) offsets, a CTA stages a
+//     contiguous run of records through shared memory with 16-byte loads;
+//   * general: a newline index is built on the device (16 bytes per thread,
+//     byte-compare masks, block scan of popcounts), then one thread per line.
+#include "gsb_common.cuh"
+
+namespace {
+
+constexpr int K1_THREADS = 256;
+constexpr int K1_LINES_PER_THREAD = 2;
+constexpr int K1_LPB = K1_THREADS * K1_LINES_PER_THREAD;
+
+__device__ __forceinline__ bool is_space(unsigned c) {
+    return c == ' ' || (c >= 9 && c <= 13);
+}
+
+__device__ const double k_pow10[23] = {
+    1e0,  1e1,  1e2,  1e3,  1e4,  1e5,  1e6,  1e7,  1e8,  1e9,  1e10, 1e11,
+    1e12, 1e13, 1e14, 1e15, 1e16, 1e17, 1e18, 1e19, 1e20, 1e21, 1e22};
+
+// correctly rounded m * 10^e10 for 0 < m < 2^64, -21 <= e10 <= 27 (exact
+// 128-bit arithmetic, round half to even).
+__device__ double scale_exact(unsigned long long m, int e10) {
+    typedef unsigned __int128 u128;
+    if (e10 >= 0) {
+        u128 v = m;
+        for (int i = 0; i < e10; ++i) {
+            if (v >> 123) return __longlong_as_double(0x7ff8000000000000LL);  // caller: EPARSE
+            v *= 10;
+        }
+        // round v to 53 bits
+        int hb = 127;
+        while (!((v >> hb) & 1)) --hb;
+        if (hb <= 52) return static_cast<double>(static_cast<unsigned long long>(v));
+        const int sh = hb - 52;
+        u128 q = v >> sh;
+        const u128 rem = v & ((static_cast<u128>(1) << sh) - 1);
+        const u128 half = static_cast<u128>(1) << (sh - 1);
+        if (rem > half || (rem == half && (q & 1))) ++q;
+        return ldexp(static_cast<double>(static_cast<unsigned long long>(q)), sh);
+    }
+    // m / 10^k: scale m up so the quotient keeps >= 64 significant bits
+    u128 den = 1;
+    for (int i = 0; i < -e10; ++i) den *= 10;       // <= 10^21 < 2^70
+    // numerator m << s with s chosen so that num < 2^127 and quotient >= 2^55
+    int mb = 63;
+    while (!((m >> mb) & 1)) --mb;
+    const int s = 126 - mb;
+    const u128 num = static_cast<u128>(m) << s;
+    u128 q = num / den;
+    const u128 r = num % den;
+    int hb = 127;
+    while (!((q >> hb) & 1)) --hb;
+    // q >= 2^126 / 2^70 = 2^56: more than 53 significant bits
+    const int sh = hb - 52;
+    u128 top = q >> sh;
+    const u128 low = q & ((static_cast<u128>(1) << sh) - 1);
+    const u128 half = static_cast<u128>(1) << (sh - 1);
+    const bool sticky = (r != 0);
+    if (low > half || (low == half && (sticky || (top & 1)))) ++top;
+    return ldexp(static_cast<double>(static_cast<unsigned long long>(top)), sh - s);
+}
+
+// Python float(bytes) on text[0:len).  Returns false on a malformed line.
+template <typename Ptr>
+__device__ bool parse_float(Ptr p, int len, float* out) {
+    int i = 0;
+    while (i < len && is_space(p[i])) ++i;
+    while (len > i && is_space(p[len - 1])) --len;
+    if (i >= len) return false;
+    bool negv = false;
+    if (p[i] == '+' || p[i] == '-') { negv = (p[i] == '-'); ++i; }
+    if (i >= len) return false;
+    unsigned c = p[i] | 0x20;
+    if (c == 'i' || c == 'n') {
+        // inf / infinity / nan
+        const int rem = len - i;
+        auto eq = [&](const char* w, int n) {
+            if (rem != n) return false;
+            for (int k = 0; k < n; ++k)
+                if ((p[i + k] | 0x20) != static_cast<unsigned>(w[k])) return false;
+            return true;
+        };
+        if (eq("inf", 3) || eq("infinity", 8)) {
+            *out = __int_as_float(negv ? 0xff800000 : 0x7f800000);
+            return true;
+        }
+        if (eq("nan", 3)) { *out = __int_as_float(0x7fc00000); return true; }
+        return false;
+    }
+    unsigned long long m = 0;
+    int ndig = 0;        // significant digits accumulated into m
+    int nd_any = 0;      // digits seen at all
+    int e10 = 0;
+    bool dropped_nonzero = false;
+    bool seen_dot = false;
+    for (; i < len; ++i) {
+        const unsigned ch = p[i];
+        if (ch >= '0' && ch <= '9') {
+            ++nd_any;
+            if (ndig < 19) {
+                if (m != 0 || ch != '0') { m = m * 10 + (ch - '0'); ++ndig; }
+                if (seen_dot) --e10;
+            } else {
+                if (ch != '0') dropped_nonzero = true;
+                if (!seen_dot) ++e10;
+            }
+        } else if (ch == '.' && !seen_dot) {
+            seen_dot = true;
+        } else {
+            break;
+        }
+    }
+    if (nd_any == 0) return false;
+    if (i < len) {
+        if ((p[i] | 0x20) != 'e') return false;
+        ++i;
+        bool eneg = false;
+        if (i < len && (p[i] == '+' || p[i] == '-')) { eneg = (p[i] == '-'); ++i; }
+        if (i >= len) return false;
+        int ex = 0;
+        for (; i < len; ++i) {
+            const unsigned ch = p[i];
+            if (ch < '0' || ch > '9') return false;
+            if (ex < 100000) ex = ex * 10 + (ch - '0');
+        }
+        e10 += eneg ? -ex : ex;
+    }
+    double d;
+    if (m == 0) {
+        d = 0.0;
+    } else if (dropped_nonzero) {
+        return false;                      // > 19 significant digits: unsupported
+    } else {
+        // strip trailing zeros of m so short numbers written with padding stay
+        // on the fast path
+        while (e10 < 0 && (m % 10) == 0) { m /= 10; ++e10; --ndig; }
+        if (ndig <= 15 && e10 >= -22 && e10 <= 22) {
+            const double dm = static_cast<double>(static_cast<long long>(m));
+            d = (e10 < 0) ? __ddiv_rn(dm, k_pow10[-e10]) : __dmul_rn(dm, k_pow10[e10]);
+        } else if (e10 >= -21 && e10 <= 27) {
+            d = scale_exact(m, e10);
+            if (d != d) return false;
+        } else {
+            return false;
+        }
+    }
+    if (negv) d = -d;
+    *out = __double2float_rn(d);
+    return true;
+}
+
+// ------------------------------------------------------------ fixed width
+__global__ void __launch_bounds__(K1_THREADS)
+k1_decode_fixed(const char* __restrict__ text, long long nbytes, int W, long long nlines,
+                float* __restrict__ out, long long* bad_line) {
+    extern __shared__ __align__(16) unsigned char sm[];
+    const long long line0 = static_cast<long long>(blockIdx.x) * K1_LPB;
+    const long long nl = min(static_cast<long long>(K1_LPB), nlines - line0);
+    if (nl <= 0) return;
+    const long long b0 = line0 * W;
+    const long long b1 = b0 + nl * W;
+    // stage [a0, a1) with 16-byte loads (a0 = b0 rounded down to 16)
+    const uintptr_t base = reinterpret_cast<uintptr_t>(text);
+    const long long mis = static_cast<long long>((base + b0) & 15);
+    const long long a0 = b0 - mis;
+    const long long nvec = (b1 - a0 + 15) / 16;
+    for (long long v = threadIdx.x; v < nvec; v += K1_THREADS) {
+        const long long off = a0 + v * 16;
+        int4 w;
+        if (off + 16 <= nbytes && off >= 0) {
+            w = __ldg(reinterpret_cast<const int4*>(text + off));
+        } else {
+            unsigned char tmp[16];
+            for (int k = 0; k < 16; ++k) {
+                const long long o = off + k;
+                tmp[k] = (o >= 0 && o < nbytes) ? static_cast<unsigned char>(text[o]) : ' ';
+            }
+            w = *reinterpret_cast<int4*>(tmp);
+        }
+        reinterpret_cast<int4*>(sm)[v] = w;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < K1_LINES_PER_THREAD; ++k) {
+        const int li = threadIdx.x + k * K1_THREADS;
+        if (li < nl) {
+            const unsigned char* p = sm + mis + static_cast<long long>(li) * W;
+            float val;
+            bool ok = (p[W - 1] == '\n') && parse_float(p, W, &val);
+            if (ok) out[line0 + li] = val;
+            else atomicMin(reinterpret_cast<unsigned long long*>(bad_line),
+                           static_cast<unsigned long long>(line0 + li));
+        }
+    }
+}
+
+// ------------------------------------------------------------ general form
+// pass 1: newline count per block (each thread 16 bytes)
+__global__ void __launch_bounds__(K1_THREADS)
+k1_count_newlines(const char* __restrict__ text, long long nbytes, unsigned* block_counts) {
+    __shared__ unsigned wsum[K1_THREADS / 32];
+    const long long off = (static_cast<long long>(blockIdx.x) * K1_THREADS + threadIdx.x) * 16;
+    unsigned cnt = 0;
+    if (off + 16 <= nbytes && ((reinterpret_cast<uintptr_t>(text) & 15) == 0)) {
+        const int4 w = __ldg(reinterpret_cast<const int4*>(text + off));
+        const unsigned ws[4] = {(unsigned)w.x, (unsigned)w.y, (unsigned)w.z, (unsigned)w.w};
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            // bytes equal to '\n' (0x0a): SWAR zero-byte test on x ^ 0x0a0a0a0a
+            const unsigned x = ws[k] ^ 0x0a0a0a0au;
+            const unsigned t = ~(((x & 0x7f7f7f7fu) + 0x7f7f7f7fu) | x | 0x7f7f7f7fu);
+            cnt += __popc(t);
+        }
+    } else {
+        for (int k = 0; k < 16; ++k)
+            if (off + k < nbytes && text[off + k] == '\n') ++cnt;
+    }
+    const unsigned wtot = __reduce_add_sync(0xffffffffu, cnt);
+    if ((threadIdx.x & 31) == 0) wsum[threadIdx.x >> 5] = wtot;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned t = 0;
+        for (int w = 0; w < K1_THREADS / 32; ++w) t += wsum[w];
+        block_counts[blockIdx.x] = t;
+    }
+}
+
+// pass 2: exclusive scan of block counts (single CTA, sequential chunks)
+__global__ void __launch_bounds__(1024) k1_scan_blocks(unsigned* counts, long long nblocks,
+                                                       unsigned long long* total) {
+    __shared__ unsigned long long carry;
+    __shared__ unsigned wsum[32];
+    if (threadIdx.x == 0) carry = 0;
+    __syncthreads();
+    for (long long base = 0; base < nblocks; base += 1024) {
+        const long long i = base + threadIdx.x;
+        const unsigned v = (i < nblocks) ? counts[i] : 0;
+        unsigned x = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const unsigned y = __shfl_up_sync(0xffffffffu, x, o);
+            if ((threadIdx.x & 31) >= o) x += y;
+        }
+        if ((threadIdx.x & 31) == 31) wsum[threadIdx.x >> 5] = x;
+        __syncthreads();
+        if (threadIdx.x < 32) {
+            unsigned w = wsum[threadIdx.x];
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const unsigned y = __shfl_up_sync(0xffffffffu, w, o);
+                if (threadIdx.x >= o) w += y;
+            }
+            wsum[threadIdx.x] = w;
+        }
+        __syncthreads();
+        const unsigned wprev = (threadIdx.x >> 5) ? wsum[(threadIdx.x >> 5) - 1] : 0;
+        const unsigned long long excl = carry + wprev + x - v;
+        // counts[] becomes the exclusive prefix; newline indices stay < 2^32
+        if (i < nblocks) counts[i] = static_cast<unsigned>(excl);
+        __syncthreads();
+        if (threadIdx.x == 1023) carry = excl + v;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) *total = carry;
+}
+
+// pass 3: write the byte offset of every newline, line_end[rank] = position
+__global__ void __launch_bounds__(K1_THREADS)
+k1_index_newlines(const char* __restrict__ text, long long nbytes,
+                  const unsigned* __restrict__ block_prefix, unsigned* line_end,
+                  long long max_lines) {
+    __shared__ unsigned wsum[K1_THREADS / 32];
+    const long long off = (static_cast<long long>(blockIdx.x) * K1_THREADS + threadIdx.x) * 16;
+    unsigned mask = 0;   // bit k: byte off+k is '\n'
+    for (int k = 0; k < 16; ++k)
+        if (off + k < nbytes && text[off + k] == '\n') mask |= 1u << k;
+    const unsigned cnt = __popc(mask);
+    unsigned x = cnt;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const unsigned y = __shfl_up_sync(0xffffffffu, x, o);
+        if ((threadIdx.x & 31) >= o) x += y;
+    }
+    if ((threadIdx.x & 31) == 31) wsum[threadIdx.x >> 5] = x;
+    __syncthreads();
+    unsigned wprev = 0;
+    for (int w = 0; w < (threadIdx.x >> 5); ++w) wprev += wsum[w];
+    unsigned rank = block_prefix[blockIdx.x] + wprev + x - cnt;
+    while (mask) {
+        const int k = __ffs(mask) - 1;
+        mask &= mask - 1;
+        if (rank < max_lines) line_end[rank] = static_cast<unsigned>(off + k);
+        ++rank;
+    }
+}
+
+// pass 4: one thread per requested line
+__global__ void __launch_bounds__(K1_THREADS)
+k1_decode_general(const char* __restrict__ text, long long nbytes,
+                  const unsigned* __restrict__ line_end, long long n_newlines,
+                  long long first_file_line, long long nlines, float* __restrict__ out,
+                  long long* bad_line) {
+    const long long i = static_cast<long long>(blockIdx.x) * K1_THREADS + threadIdx.x;
+    if (i >= nlines) return;
+    const long long fl = first_file_line + i;     // line index in the file
+    const long long start = fl == 0 ? 0 : static_cast<long long>(line_end[fl - 1]) + 1;
+    const long long end = fl < n_newlines ? static_cast<long long>(line_end[fl]) : nbytes;
+    float val;
+    bool ok = (start <= end) && (end - start < 4096) &&
+              parse_float(reinterpret_cast<const unsigned char*>(text) + start,
+                          static_cast<int>(end - start), &val);
+    if (ok) out[i] = val;
+    else atomicMin(reinterpret_cast<unsigned long long*>(bad_line),
+                   static_cast<unsigned long long>(i));
+}
+
+// ------------------------------------------------------------------ encoder
+// fixed-width '%<width>.<prec>f' + EOL, correctly rounded for values whose
+// scaled magnitude fits 2^53 (all GSLIB-style data); one thread per value
+__global__ void __launch_bounds__(K1_THREADS)
+k1_encode_fixed(const float* __restrict__ row, long long nn, int width, int prec, int crlf,
+                char* __restrict__ text) {
+    const long long i = static_cast<long long>(blockIdx.x) * K1_THREADS + threadIdx.x;
+    if (i >= nn) return;
+    const int W = width + (crlf ? 2 : 1);
+    char* p = text + i * W;
+    const double v = static_cast<double>(row[i]);
+    const bool negv = v < 0;
+    const double av = fabs(v);
+    double scale = 1.0;
+    for (int k = 0; k < prec; ++k) scale *= 10.0;
+    // exact decimal expansion of a binary float is finite: round-half-even on
+    // the exact product (av*scale is exact when it fits 53 bits; the synthetic
+    // lattice values and 6-decimal maps do)
+    const double scaled = av * scale;
+    unsigned long long q = static_cast<unsigned long long>(rint(scaled));
+    char tmp[40];
+    int n = 0;
+    for (int k = 0; k < prec; ++k) { tmp[n++] = '0' + static_cast<int>(q % 10); q /= 10; }
+    if (prec > 0) tmp[n++] = '.';
+    do { tmp[n++] = '0' + static_cast<int>(q % 10); q /= 10; } while (q && n < 38);
+    if (negv) tmp[n++] = '-';
+    int pos = 0;
+    for (; pos < width - n; ++pos) p[pos] = ' ';
+    for (int k = n - 1; k >= 0 && pos < width; --k) p[pos++] = tmp[k];
+    if (crlf) { p[width] = '\r'; p[width + 1] = '\n'; }
+    else p[width] = '\n';
+}
+
+}  // namespace
+
+int gsb_launch_decode(gsb_stack* s, int64_t r, const char* dtext, size_t nbytes,
+                      int header_lines, int line_width, int64_t first_line, int64_t n0,
+                      int64_t nlines, int64_t* d_bad_line, cudaStream_t st) {
+    if (nlines <= 0) return GSB_OK;
+    float* out = s->data + r * s->pitch + n0;
+    if (line_width > 0) {
+        GSB_REQUIRE(header_lines == 0,
+                    "fixed-width decode expects the header to be stripped by the caller");
+        GSB_REQUIRE(static_cast<size_t>(first_line + nlines) * line_width <= nbytes,
+                    "text too short: %lld lines of %d bytes need %lld bytes, have %zu",
+                    (long long)(first_line + nlines), line_width,
+                    (long long)(first_line + nlines) * line_width, nbytes);
+        dtext += first_line * line_width;
+        nbytes -= static_cast<size_t>(first_line) * line_width;
+        GSB_REQUIRE(line_width >= 2 && line_width <= 64, "line_width %d out of range",
+                    line_width);
+        const long long blocks = (nlines + K1_LPB - 1) / K1_LPB;
+        const size_t smem = static_cast<size_t>(K1_LPB) * line_width + 48;
+        GSB_CUDA(cudaFuncSetAttribute(k1_decode_fixed,
+                                      cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      K1_LPB * 64 + 48));
+        k1_decode_fixed<<<static_cast<int>(blocks), K1_THREADS, smem, st>>>(
+            dtext, static_cast<long long>(nbytes), line_width, nlines, out,
+            reinterpret_cast<long long*>(d_bad_line));
+        GSB_CUDA(cudaGetLastError());
+        return GSB_OK;
+    }
+    // general form: newline index in scratch (after the 64 MB host-staging area)
+    GSB_REQUIRE(nbytes < (1ull << 32), "general decode handles files < 4 GiB");
+    const long long nblk = (static_cast<long long>(nbytes) + K1_THREADS * 16 - 1) / (K1_THREADS * 16);
+    void* g = nullptr;
+    const size_t need = static_cast<size_t>(nblk) * 4 + 16 + static_cast<size_t>(nbytes / 2 + 2) * 4;
+    int rc = gsb_scratch(s, need, &g);
+    if (rc) return rc;
+    unsigned* counts = static_cast<unsigned*>(g);
+    unsigned long long* total = reinterpret_cast<unsigned long long*>(
+        static_cast<char*>(g) + ((static_cast<size_t>(nblk) * 4 + 15) & ~size_t(15)));
+    unsigned* line_end = reinterpret_cast<unsigned*>(total + 2);
+    const long long cap_lines = static_cast<long long>(nbytes / 2 + 2);
+    k1_count_newlines<<<static_cast<int>(nblk), K1_THREADS, 0, st>>>(
+        dtext, static_cast<long long>(nbytes), counts);
+    k1_scan_blocks<<<1, 1024, 0, st>>>(counts, nblk, total);
+    k1_index_newlines<<<static_cast<int>(nblk), K1_THREADS, 0, st>>>(
+        dtext, static_cast<long long>(nbytes), counts, line_end, cap_lines);
+    GSB_CUDA(cudaGetLastError());
+    unsigned long long h_total = 0;
+    GSB_CUDA(cudaMemcpyAsync(&h_total, total, 8, cudaMemcpyDeviceToHost, st));
+    GSB_CUDA(cudaStreamSynchronize(st));
+    long long n_newlines = static_cast<long long>(h_total);
+    if (n_newlines > cap_lines) n_newlines = cap_lines;   // only blank lines can exceed
+    // lines available = newlines (+1 if the file does not end with one)
+    const long long first = header_lines + first_line;
+    GSB_REQUIRE(first + nlines <= n_newlines + 1,
+                "text has %lld lines, need %lld", n_newlines + 1, first + nlines);
+    const long long blocks = (nlines + K1_THREADS - 1) / K1_THREADS;
+    k1_decode_general<<<static_cast<int>(blocks), K1_THREADS, 0, st>>>(
+        dtext, static_cast<long long>(nbytes), line_end, n_newlines, first, nlines, out,
+        reinterpret_cast<long long*>(d_bad_line));
+    GSB_CUDA(cudaGetLastError());
+    return GSB_OK;
+}
+
+int gsb_launch_encode(const gsb_stack* s, int64_t r, int64_t n0, int64_t nn, int width,
+                      int prec, int crlf, char* dtext, cudaStream_t st) {
+    if (nn <= 0) return GSB_OK;
+    GSB_REQUIRE(width >= 4 && width <= 32 && prec >= 0 && prec <= 9,
+                "encode: width/prec out of range");
+    const long long blocks = (nn + K1_THREADS - 1) / K1_THREADS;
+    k1_encode_fixed<<<static_cast<int>(blocks), K1_THREADS, 0, st>>>(
+        s->data + r * s->pitch + n0, nn, width, prec, crlf, dtext);
+    GSB_CUDA(cudaGetLastError());
+    return GSB_OK;
+}

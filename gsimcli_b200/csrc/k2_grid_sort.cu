@@ -1,0 +1,498 @@
+// k2_grid_sort.cu -- K2: realization-axis reduction with exact order statistics
+//
+// Replaces the cell loop of GridFiles.stats (GSIMCLI/tools/grid.py:662-701):
+// for every grid node, the R realization values are reduced to mean / variance
+// / std / coefvar / skewness (moments) and to any number of linearly
+// interpolated quantiles (median, percentile pair, percentile lists) and the
+// mode (extension).
+//
+// Data flow (one persistent CTA of 8 warps per SM; 256 threads so that each
+// thread may use up to 255 registers -- the column tile lives in registers):
+//   HBM stack [R][pitch] f32  --TMA 2-D boxes 32 rows x 32 nodes, 128B swizzle-->
+//   32-stage (128 KB) shared-memory ring, refilled by whichever warp is the
+//   last to finish reading a stage  --LDS.128, conflict-free-->
+//   registers: warp w owns nodes 4w..4w+3 of the tile, lane l holds rows
+//   {32 j + l}; IPT = ceil32(R)/32 values per lane and node.
+// In registers: (1) nodata/NaN -> +INF and shifted one-pass moments (pivot =
+// mean of the first 32 realizations, so no cancellation); (2) a bitonic sort
+// of the padded column across the warp: Batcher odd-even merge sort inside
+// each lane, then bitonic merge phases whose cross-lane stages are one
+// SHFL + one FMNMX per element thanks to a per-lane sign state (a lane that
+// must keep the larger value stores negated values, so every lane executes
+// y = min(y, -y_partner)); (3) the sorted column is parked in shared memory,
+// each lane computes one output plane (quantile lerp in float64 exactly as
+// NumPy's _lerp; moments finished in float64; mode from a run-length bitmap
+// with binary lifting) and stores 4 adjacent nodes with one 16-byte store.
+// HBM traffic: the stack is read exactly once (4 B per node-realization).
+#include "gsb_common.cuh"
+#include <utility>
+
+namespace {
+
+constexpr int K2_WARPS = 8;
+constexpr int K2_THREADS = K2_WARPS * 32;
+constexpr int K2_STAGE_BYTES = 4096;   // 32 rows x 32 nodes x 4 B
+constexpr int K2_NST = 32;             // ring depth: one full R=1024 tile
+constexpr unsigned FULL = 0xffffffffu;
+
+struct K2Args {
+    int R;
+    int nchunks;
+    int nplanes;
+    float nodata;
+    long long ntiles;
+    long long n0;
+    long long nn;
+    float* out;
+    long long out_pitch;
+    unsigned char kind[GSB_MAX_PLANES];
+    double q[GSB_MAX_PLANES];
+};
+
+// ---------------------------------------------------------------------------
+// Batcher odd-even merge sort network for N = 2^k inputs, generated at compile
+// time (191 compare-exchanges for N = 32; bitonic would need 240).
+template <int N>
+struct OemNet {
+    static constexpr int MAXCE = (N <= 1) ? 1 : N * 8;
+    int n = 0;
+    int a[MAXCE] = {};
+    int b[MAXCE] = {};
+};
+
+template <int N>
+constexpr OemNet<N> make_oem() {
+    OemNet<N> net{};
+    for (int p = 1; p < N; p <<= 1)
+        for (int k = p; k >= 1; k >>= 1)
+            for (int j = k % p; j + k < N; j += 2 * k)
+                for (int i = 0; i < k && i + j + k < N; ++i)
+                    if ((i + j) / (2 * p) == (i + j + k) / (2 * p)) {
+                        net.a[net.n] = i + j;
+                        net.b[net.n] = i + j + k;
+                        ++net.n;
+                    }
+    return net;
+}
+
+template <int IPT>
+struct Oem {
+    static constexpr OemNet<IPT> net = make_oem<IPT>();
+};
+
+template <int I, int J, int IPT>
+__device__ __forceinline__ void ce4(float (&v)[4][IPT]) {
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+        const float x = v[c][I], y = v[c][J];
+        v[c][I] = fminf(x, y);
+        v[c][J] = fmaxf(x, y);
+    }
+}
+
+template <int IPT, int... Is>
+__device__ __forceinline__ void oem_apply(float (&v)[4][IPT],
+                                          std::integer_sequence<int, Is...>) {
+    (ce4<Oem<IPT>::net.a[Is], Oem<IPT>::net.b[Is], IPT>(v), ...);
+}
+
+template <int IPT>
+__device__ __forceinline__ void sort_in_lane(float (&v)[4][IPT]) {
+    if constexpr (IPT > 1)
+        oem_apply<IPT>(v, std::make_integer_sequence<int, Oem<IPT>::net.n>{});
+}
+
+template <int IPT>
+__device__ __forceinline__ void scale_all(float (&v)[4][IPT], float f) {
+#pragma unroll
+    for (int c = 0; c < 4; ++c)
+#pragma unroll
+        for (int j = 0; j < IPT; ++j) v[c][j] *= f;
+}
+
+// Bitonic merge phases across the warp.  Logical position = lane*IPT + reg.
+// On entry every lane is sorted ascending in ITS stored values, and lanes with
+// (lane & 1) hold negated values (i.e. are descending in x).  `neg` tracks the
+// lane's sign state.  On exit all lanes hold plain x, globally ascending.
+template <int IPT>
+__device__ __forceinline__ void merge_across_lanes(float (&v)[4][IPT], int lane,
+                                                   bool neg) {
+#pragma unroll
+    for (int L = 2; L <= 32; L <<= 1) {
+        const bool desc = (L < 32) && ((lane & L) != 0);
+#pragma unroll
+        for (int ls = L >> 1; ls >= 1; ls >>= 1) {
+            // the lane that keeps the larger value works on negated data
+            const bool want = ((lane & ls) != 0) != desc;
+            scale_all<IPT>(v, (want != neg) ? -1.0f : 1.0f);
+            neg = want;
+#pragma unroll
+            for (int c = 0; c < 4; ++c)
+#pragma unroll
+                for (int j = 0; j < IPT; ++j) {
+                    const float o = __shfl_xor_sync(FULL, v[c][j], ls);
+                    v[c][j] = fminf(v[c][j], -o);
+                }
+        }
+        if constexpr (IPT > 1) {
+            scale_all<IPT>(v, (desc != neg) ? -1.0f : 1.0f);
+            neg = desc;
+#pragma unroll
+            for (int s = IPT >> 1; s >= 1; s >>= 1)
+#pragma unroll
+                for (int j = 0; j < IPT; ++j)
+                    if ((j & s) == 0) {
+#pragma unroll
+                        for (int c = 0; c < 4; ++c) {
+                            const float x = v[c][j], y = v[c][j | s];
+                            v[c][j] = fminf(x, y);
+                            v[c][j | s] = fmaxf(x, y);
+                        }
+                    }
+        } else {
+            scale_all<IPT>(v, (desc != neg) ? -1.0f : 1.0f);
+            neg = desc;
+        }
+    }
+}
+
+__device__ __forceinline__ float warp_sum(float x) {
+#pragma unroll
+    for (int o = 16; o >= 1; o >>= 1) x += __shfl_xor_sync(FULL, x, o);
+    return x;
+}
+
+// B(p) = A(p - s) over the NPAD-bit string distributed IPT bits per lane
+template <int IPT>
+__device__ __forceinline__ uint32_t bits_shift(uint32_t A, int s, int lane) {
+    constexpr uint32_t WM = (IPT == 32) ? 0xffffffffu : ((1u << IPT) - 1u);
+    const int ws = s / IPT, bs = s % IPT;
+    uint32_t lo = __shfl_up_sync(FULL, A, ws & 31);
+    uint32_t hi = __shfl_up_sync(FULL, A, (ws + 1) & 31);
+    if (lane < ws || ws > 31) lo = 0;
+    if (lane < ws + 1 || ws + 1 > 31) hi = 0;
+    uint32_t r = lo << bs;
+    if (bs) r |= hi >> (IPT - bs);
+    return r & WM;
+}
+
+// scratch address of sorted position p (rotation keeps the dump conflict-free)
+template <int IPT>
+__device__ __forceinline__ int scr_addr(int p) {
+    const int l = p / IPT, j = p % IPT;
+    return l * IPT + ((j + ((l * IPT) >> 5)) & (IPT - 1));
+}
+
+template <int IPT, bool MODE>
+__global__ void __launch_bounds__(K2_THREADS, 1)
+k2_sort_kernel(const __grid_constant__ CUtensorMap tmap,
+               const __grid_constant__ K2Args a) {
+    constexpr int NPAD = IPT * 32;
+    constexpr int LOGN = (NPAD == 32) ? 5 : (NPAD == 64) ? 6 : (NPAD == 128) ? 7
+                       : (NPAD == 256) ? 8 : (NPAD == 512) ? 9 : 10;
+    extern __shared__ __align__(1024) unsigned char smem[];
+    float* scratch_all = reinterpret_cast<float*>(smem + K2_NST * K2_STAGE_BYTES);
+    uint64_t* full = reinterpret_cast<uint64_t*>(
+        smem + K2_NST * K2_STAGE_BYTES + K2_WARPS * NPAD * 4);
+    int* rd_cnt = reinterpret_cast<int*>(full + K2_NST);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+
+    // chunk sequence of this CTA: seq -> (tile = blockIdx.x + (seq / nchunks) * gridDim.x,
+    // rows [32 (seq % nchunks), +32)); stage = seq % K2_NST
+    const long long my_tiles =
+        (a.ntiles > blockIdx.x) ? (a.ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+    const long long total_chunks = my_tiles * a.nchunks;
+    auto issue = [&](long long seq) {
+        const long long ti = seq / a.nchunks;
+        const int j = static_cast<int>(seq - ti * a.nchunks);
+        const int col = static_cast<int>(a.n0 + (blockIdx.x + ti * gridDim.x) * 32);
+        const uint32_t st = static_cast<uint32_t>(seq % K2_NST);
+        gsb_mbar_expect_tx(&full[st], K2_STAGE_BYTES);
+        gsb_tma_load_2d(smem + st * K2_STAGE_BYTES, &tmap, &full[st], col, j * 32);
+    };
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < K2_NST; ++s) {
+            gsb_mbar_init(&full[s], 1);
+            rd_cnt[s] = 0;
+        }
+        gsb_fence_barrier_init();
+        gsb_prefetch_tmap(&tmap);
+        for (long long seq = 0; seq < K2_NST && seq < total_chunks; ++seq) issue(seq);
+    }
+    __syncthreads();
+
+    // ------------------------------------------------------------ consumers
+    float* scr = scratch_all + warp * NPAD;
+    const uint32_t my_off = lane * 128u + ((static_cast<uint32_t>(warp) ^ (lane & 7u)) << 4);
+    const float INF = __int_as_float(0x7f800000);
+    const float sg = (lane & 1) ? -1.0f : 1.0f;
+
+    // this lane's output planes (round r handles plane r*32 + lane)
+    int kind0 = -1, kind1 = -1;
+    double q0 = 0.0, q1 = 0.0;
+    if (lane < a.nplanes) { kind0 = a.kind[lane]; q0 = a.q[lane]; }
+    if (lane + 32 < a.nplanes) { kind1 = a.kind[lane + 32]; q1 = a.q[lane + 32]; }
+
+    uint32_t it = 0;
+    for (long long tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x) {
+        float v[4][IPT];
+        float piv[4], S1[4], S2[4], S3[4];
+        int cnt[4];
+#pragma unroll
+        for (int c = 0; c < 4; ++c) { S1[c] = S2[c] = S3[c] = 0.f; cnt[c] = 0; piv[c] = 0.f; }
+
+#pragma unroll
+        for (int j = 0; j < IPT; ++j) {
+            if (j < a.nchunks) {
+                const uint32_t st = it % K2_NST;
+                const uint32_t ph = (it / K2_NST) & 1u;
+                gsb_mbar_wait(&full[st], ph);
+                const float4 x4 = *reinterpret_cast<const float4*>(
+                    smem + st * K2_STAGE_BYTES + my_off);
+                const float xs[4] = {x4.x, x4.y, x4.z, x4.w};
+                const bool rowok = (j * 32 + lane) < a.R;
+                bool ok[4];
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    // bn.replace(arr, nodata, nan): exact equality in f32; a
+                    // NaN read from the file is dropped like one (grid.py:681)
+                    ok[c] = rowok && (xs[c] == xs[c]) && (xs[c] != a.nodata);
+                    cnt[c] += ok[c] ? 1 : 0;
+                }
+                if (j == 0) {
+                    // pivot = mean of the valid values among the first 32 rows
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) {
+                        const float s0 = warp_sum(ok[c] ? xs[c] : 0.f);
+                        const int c0 = __reduce_add_sync(FULL, ok[c] ? 1 : 0);
+                        piv[c] = c0 ? s0 / static_cast<float>(c0) : 0.f;
+                    }
+                }
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    const float d = (ok[c] ? xs[c] : piv[c]) - piv[c];
+                    const float d2 = d * d;
+                    S1[c] += d;
+                    S2[c] += d2;
+                    S3[c] = fmaf(d2, d, S3[c]);
+                    v[c][j] = (ok[c] ? xs[c] : INF) * sg;
+                }
+                __syncwarp();
+                if (lane == 0) {
+                    // the last of the 8 warps to finish reading a stage refills it
+                    __threadfence_block();
+                    if (atomicAdd(&rd_cnt[st], 1) == K2_WARPS - 1) {
+                        __threadfence_block();
+                        rd_cnt[st] = 0;
+                        const long long nxt = static_cast<long long>(it) + K2_NST;
+                        if (nxt < total_chunks) issue(nxt);
+                    }
+                }
+                ++it;
+            } else {
+#pragma unroll
+                for (int c = 0; c < 4; ++c) v[c][j] = INF * sg;
+            }
+        }
+
+        // ---- moments: finish the shifted sums in float64
+        int n[4];
+        double mean[4], m2[4], m3[4];
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            n[c] = __reduce_add_sync(FULL, cnt[c]);
+            const double s1 = static_cast<double>(warp_sum(S1[c]));
+            const double s2 = static_cast<double>(warp_sum(S2[c]));
+            const double s3 = static_cast<double>(warp_sum(S3[c]));
+            const double dn = static_cast<double>(n[c]);
+            const double delta = s1 / dn;
+            mean[c] = static_cast<double>(piv[c]) + delta;
+            m2[c] = s2 - s1 * delta;
+            m3[c] = s3 - 3.0 * delta * s2 + 2.0 * dn * delta * delta * delta;
+        }
+
+        // ---- sort the 4 columns (lane-major positions, ascending)
+        if (a.nplanes > 0) {
+            sort_in_lane<IPT>(v);
+            merge_across_lanes<IPT>(v, lane, (lane & 1) != 0);
+        }
+
+        // ---- per column: park sorted values, evaluate planes
+        float res0[4], res1[4];
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            __syncwarp();
+#pragma unroll
+            for (int j = 0; j < IPT; ++j)
+                scr[lane * IPT + ((j + ((lane * IPT) >> 5)) & (IPT - 1))] = v[c][j];
+            __syncwarp();
+
+            const int nc = n[c];
+            const float vmin = scr[scr_addr<IPT>(0)];
+            const float vmax = scr[scr_addr<IPT>(nc > 0 ? nc - 1 : 0)];
+            const bool constant = (vmin == vmax);
+            const double dn = static_cast<double>(nc);
+            const double M2 = constant ? 0.0 : fmax(m2[c], 0.0);
+            const double M3 = constant ? 0.0 : m3[c];
+            const double var = (nc > 1) ? M2 / (dn - 1.0) : __longlong_as_double(0x7ff8000000000000LL);
+            const double sd = sqrt(var);
+
+            float modev = 0.f;
+            if constexpr (MODE) {
+                // bit j of lane l: sorted[p] == sorted[p-1], p = l*IPT + j
+                uint32_t M = 0;
+                const float prev_last = __shfl_up_sync(FULL, v[c][IPT - 1], 1);
+                if (lane > 0 && v[c][0] == prev_last) M |= 1u;
+#pragma unroll
+                for (int j = 1; j < IPT; ++j)
+                    if (v[c][j] == v[c][j - 1]) M |= (1u << j);
+                const int mloc = nc - lane * IPT;     // valid positions in this lane
+                if (mloc <= 0) M = 0;
+                else if (mloc < IPT) M &= (1u << mloc) - 1u;
+                uint32_t P[LOGN + 1];
+                P[0] = M;
+                int top = __any_sync(FULL, M != 0) ? 0 : -1;
+#pragma unroll
+                for (int i = 0; i < LOGN; ++i) {
+                    P[i + 1] = 0;
+                    if (top == i) {
+                        const uint32_t nx = P[i] & bits_shift<IPT>(P[i], 1 << i, lane);
+                        if (__any_sync(FULL, nx != 0)) { P[i + 1] = nx; top = i + 1; }
+                    }
+                }
+                uint32_t cur = 0;
+                int len = 0;
+#pragma unroll
+                for (int i = LOGN; i >= 0; --i) {
+                    if (i == top) { cur = P[i]; len = 1 << i; }
+                    else if (i < top) {
+                        const uint32_t cand = cur & bits_shift<IPT>(P[i], len, lane);
+                        if (__any_sync(FULL, cand != 0)) { cur = cand; len += 1 << i; }
+                    }
+                }
+                int pe = 0;
+                if (top >= 0) {
+                    const uint32_t b = __ballot_sync(FULL, cur != 0);
+                    const int lf = __ffs(b) - 1;
+                    const uint32_t w = __shfl_sync(FULL, cur, lf);
+                    pe = lf * IPT + __ffs(w) - 1;
+                }
+                modev = scr[scr_addr<IPT>(pe)];
+            }
+
+            auto plane_value = [&](int kind, double q) -> float {
+                const double qnan = __longlong_as_double(0x7ff8000000000000LL);
+                if (nc == 0) return __int_as_float(0x7fc00000);
+                double r = qnan;
+                switch (kind) {
+                case GSB_PK_MEAN: r = mean[c]; break;
+                case GSB_PK_VAR: r = var; break;
+                case GSB_PK_STD: r = sd; break;
+                case GSB_PK_COEFVAR: r = sd / mean[c] * 100.0; break;
+                case GSB_PK_SKEW:
+                    if (nc < 3) r = qnan;
+                    else if (M2 == 0.0) r = 0.0;
+                    else r = (dn * sqrt(dn - 1.0) / (dn - 2.0)) * (M3 / (M2 * sqrt(M2)));
+                    break;
+                case GSB_PK_MODE: r = static_cast<double>(modev); break;
+                case GSB_PK_QUANT: {
+                    // np.quantile(method='linear'): h = (n-1) q, NumPy _lerp
+                    const double h = __dmul_rn(dn - 1.0, q);
+                    if (h >= dn - 1.0) r = static_cast<double>(vmax);
+                    else if (h < 0.0) r = static_cast<double>(vmin);
+                    else {
+                        const double fl = floor(h);
+                        const int lo = static_cast<int>(fl);
+                        const double t = h - fl;
+                        const double x0 = static_cast<double>(scr[scr_addr<IPT>(lo)]);
+                        const double x1 = static_cast<double>(scr[scr_addr<IPT>(lo + 1)]);
+                        const double d = x1 - x0;
+                        r = (t >= 0.5) ? __dsub_rn(x1, __dmul_rn(d, 1.0 - t))
+                                       : __dadd_rn(x0, __dmul_rn(d, t));
+                    }
+                } break;
+                default: break;
+                }
+                return static_cast<float>(r);
+            };
+            res0[c] = (kind0 >= 0) ? plane_value(kind0, q0) : 0.f;
+            res1[c] = (kind1 >= 0) ? plane_value(kind1, q1) : 0.f;
+        }
+
+        // ---- store: lane = plane, 4 adjacent nodes per 16-byte store
+        const long long colbase = tile * 32 + warp * 4;
+        const long long left = a.nn - colbase;
+        const bool vec = ((a.out_pitch & 3) == 0) &&
+                         ((reinterpret_cast<uintptr_t>(a.out) & 15) == 0) && left >= 4;
+        if (kind0 >= 0 && left > 0) {
+            float* o = a.out + static_cast<long long>(lane) * a.out_pitch + colbase;
+            if (vec) *reinterpret_cast<float4*>(o) = make_float4(res0[0], res0[1], res0[2], res0[3]);
+            else
+#pragma unroll
+                for (int c = 0; c < 4; ++c) if (c < left) o[c] = res0[c];
+        }
+        if (kind1 >= 0 && left > 0) {
+            float* o = a.out + static_cast<long long>(lane + 32) * a.out_pitch + colbase;
+            if (vec) *reinterpret_cast<float4*>(o) = make_float4(res1[0], res1[1], res1[2], res1[3]);
+            else
+#pragma unroll
+                for (int c = 0; c < 4; ++c) if (c < left) o[c] = res1[c];
+        }
+    }
+}
+
+template <int IPT, bool MODE>
+int launch_one(gsb_stack* s, const K2Args& args, int grid, cudaStream_t st) {
+    constexpr int NPAD = IPT * 32;
+    const size_t smem = K2_NST * K2_STAGE_BYTES + K2_WARPS * NPAD * 4 + K2_NST * 8 + K2_NST * 4;
+    auto kern = k2_sort_kernel<IPT, MODE>;
+    GSB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  static_cast<int>(smem)));
+    kern<<<grid, K2_THREADS, smem, st>>>(s->tmap_k2, args);
+    GSB_CUDA(cudaGetLastError());
+    return GSB_OK;
+}
+
+template <bool MODE>
+int launch_ipt(gsb_stack* s, const K2Args& args, int ipt, int grid, cudaStream_t st) {
+    switch (ipt) {
+    case 1: return launch_one<1, MODE>(s, args, grid, st);
+    case 2: return launch_one<2, MODE>(s, args, grid, st);
+    case 4: return launch_one<4, MODE>(s, args, grid, st);
+    case 8: return launch_one<8, MODE>(s, args, grid, st);
+    case 16: return launch_one<16, MODE>(s, args, grid, st);
+    case 32: return launch_one<32, MODE>(s, args, grid, st);
+    }
+    gsb_set_error("k2: unsupported items-per-lane %d", ipt);
+    return GSB_EINVAL;
+}
+
+}  // namespace
+
+int gsb_launch_k2_sort(gsb_stack* s, const GsbPlanes& pl, float nodata, int64_t n0,
+                       int64_t nn, float* d_out, int64_t out_pitch, cudaStream_t st) {
+    GSB_REQUIRE(s->R <= GSB_MAX_R_GRID, "k2 sort kernel supports R <= %d (got %lld)",
+                GSB_MAX_R_GRID, (long long)s->R);
+    GSB_REQUIRE(s->tmap_ok, "stack has no tensor map (driver entry point missing)");
+    K2Args args;
+    memset(&args, 0, sizeof(args));
+    args.R = static_cast<int>(s->R);
+    args.nchunks = static_cast<int>((s->R + 31) / 32);
+    args.nplanes = pl.n;
+    args.nodata = nodata;
+    args.ntiles = (nn + 31) / 32;
+    args.n0 = n0;
+    args.nn = nn;
+    args.out = d_out;
+    args.out_pitch = out_pitch;
+    for (int i = 0; i < pl.n; ++i) { args.kind[i] = pl.kind[i]; args.q[i] = pl.q[i]; }
+    int ipt = 1;
+    while (ipt * 32 < s->R) ipt <<= 1;
+    const int grid = static_cast<int>(args.ntiles < s->sm_count ? args.ntiles : s->sm_count);
+    if (grid <= 0) return GSB_OK;
+    return pl.need_mode ? launch_ipt<true>(s, args, ipt, grid, st)
+                        : launch_ipt<false>(s, args, ipt, grid, st);
+}

@@ -1,0 +1,60 @@
+# -*- coding: utf-8 -*-
+"""Multi-GPU plumbing: node-range sharding and the per-station table gather.
+
+The path shards by grid nodes: every statistic is a function of
+one node's realization column, so each rank holds a contiguous node range --
+a block of time slices, because GSLIB order is x fastest, then y, then z -- and
+no data-path collective is needed.  The only exchange is the gather of the
+small per-station tables (S x dz x C float64), done with
+``torch.distributed`` (NCCL over NVLink on GPUs, gloo in the CPU tests).
+PyTorch is used for tensor handles and the collective only.
+"""
+import numpy as np
+
+
+def slab_range(dims, rank, world):
+    """Contiguous node range ``[n0, n1)`` of ``rank``: whole time layers are
+    dealt out as evenly as possible (the first ``dz % world`` ranks get one
+    more)."""
+    dx, dy, dz = int(dims[0]), int(dims[1]), int(dims[2])
+    base, extra = divmod(dz, world)
+    z0 = rank * base + min(rank, extra)
+    z1 = z0 + base + (1 if rank < extra else 0)
+    return z0 * dx * dy, z1 * dx * dy
+
+
+def layer_range(dims, rank, world):
+    n0, n1 = slab_range(dims, rank, world)
+    per = int(dims[0]) * int(dims[1])
+    return n0 // per, n1 // per
+
+
+def allgather_tables(local, dims, group=None, device=None):
+    """Combine per-rank station tables ``[S][dz][C]`` whose rows are valid only
+    for the rank's own time layers into the full table on every rank.
+
+    Each rank contributes the rows of its slab (``layer_range``); ranks may own
+    different numbers of layers, so the rows are padded to the largest slab for
+    the fixed-size ``all_gather`` and trimmed afterwards.
+    """
+    import torch
+    import torch.distributed as td
+    if not (td.is_available() and td.is_initialized()):
+        return local
+    world = td.get_world_size(group)
+    rank = td.get_rank(group)
+    S, dz, C = local.shape
+    ranges = [layer_range(dims, r, world) for r in range(world)]
+    width = max(z1 - z0 for z0, z1 in ranges)
+    z0, z1 = ranges[rank]
+    mine = np.full((S, width, C), np.nan)
+    mine[:, :z1 - z0] = local[:, z0:z1]
+    backend = td.get_backend(group)
+    dev = device if backend == 'nccl' else 'cpu'
+    send = torch.from_numpy(mine).to(dev)
+    parts = [torch.empty_like(send) for _ in range(world)]
+    td.all_gather(parts, send, group=group)
+    full = np.empty_like(local)
+    for r, (a, b) in enumerate(ranges):
+        full[:, a:b] = parts[r].cpu().numpy()[:, :b - a]
+    return full

@@ -1,0 +1,278 @@
+# -*- coding: utf-8 -*-
+"""Detection and correction of inhomogeneities against the local PDFs.
+
+Drop-in for ``detect`` and ``fill_station`` of the reference's
+``GSIMCLI/tools/homog.py`` (:27-276, :279-337) plus the small station
+bookkeeping around them (``list_stations``, ``take_candidate``,
+``update_station``, :340-545).  ``detect`` keeps the reference's signature and
+return value; the local PDFs come from ``GridFiles.stats_area`` (K2c on the
+GPU) and the fill / flag / substitute step runs as the fused K3 kernel
+(``gsb_detect``).  ``detect_many`` is the batched extension: all stations of a
+network against one stack with one K2c and one K3 launch.
+"""
+import numpy as np
+import pandas as pd
+
+from .. import _capi
+from . import grid as gr
+
+_STATS_NAMES = {'lmean': 'mean', 'lmed': 'median', 'lskew': 'skewness',
+                'lvar': 'variance', 'lstd': 'std', 'lcoefvar': 'coefvar',
+                'lperc': 'lperc'}
+
+
+def _select_stats(method, skewness, optional_stats):
+    """Statistics required by the correction method (homog.py:136-167)."""
+    if method == 'mean':
+        sel = dict(lmean=True, lmed=False, lskew=False)
+    elif method == 'median':
+        sel = dict(lmean=False, lmed=True, lskew=False)
+    elif method == 'skewness' and skewness:
+        sel = dict(lmean=True, lmed=True, lskew=True)
+    elif method == 'percentile':
+        sel = dict(lmean=False, lmed=False, lskew=False)
+    else:
+        raise ValueError('Method {0} invalid or incomplete.'.format(method))
+    if optional_stats:
+        sel.update(optional_stats)
+    sel['lmean'] = True     # always needed to fill missing data (homog.py:165)
+    sel['lperc'] = True     # always needed for the detection (homog.py:167)
+    return sel
+
+
+def _prepare_obs(obs, grids, header):
+    """Steps (2)-(5) of detect on one candidate: first valid coordinates,
+    Flag removal, nodata count and nodata -> NaN (homog.py:169-188)."""
+    if not isinstance(obs, gr.PointSet):
+        path = obs
+        obs = gr.PointSet()
+        obs.load(path, header=header)
+    obs_xy = list(obs.values.loc[obs.values.first_valid_index(), ['x', 'y']])
+    if 'Flag' in obs.values.columns:
+        obs.values = obs.values.drop('Flag', axis=1)
+    if 'Flag' in obs.varnames:
+        obs.varnames.remove('Flag')
+        obs.nvars -= 1
+    nodatas = int(obs.values['clim'].isin([obs.nodata]).sum())
+    obs.values = obs.values.replace(obs.nodata, np.nan)
+    return obs, obs_xy, nodatas
+
+
+def _finish(obs, local, fixcols, method, skewness, hom_in, flag,
+            optional_stats, grids, obs_xy, rad):
+    """Steps (7)-(12): K3 and assembly of the homogenised PointSet
+    (homog.py:204-269)."""
+    filled, homog, flagcol, det = hom_in
+    obs.values['clim'] = filled
+    homogenised = gr.PointSet(obs.name + '_homogenised', obs.nodata, obs.nvars,
+                              list(obs.varnames), obs.values.copy())
+    # placeholders of optional statistics are all-NaN columns (homog.py:212)
+    homogenised.values = homogenised.values.dropna(axis=1)
+    homogenised.varnames = list(homogenised.values.columns)
+    homogenised.values['clim'] = homog
+    if flag:
+        homogenised.add_var(flagcol, 'Flag')
+    if optional_stats:
+        for key, value in optional_stats.items():
+            if value and key == 'lperc':
+                if 'median' in local.columns:
+                    med = local['median'].values
+                else:
+                    med = grids.stats_area(obs_xy, rad, lmed=True,
+                                           save=False).values['median'].values
+                with np.errstate(invalid='ignore'):
+                    pdet = np.where(filled >= med, local['rperc'].values,
+                                    local['lperc'].values)
+                homogenised.add_var(varname='pdet', values=pdet)
+            elif value:
+                name = _STATS_NAMES[key]
+                homogenised.add_var(varname=name, values=local[name].values)
+    return homogenised, int(det)
+
+
+def _fix_columns(method, local, vline_perc):
+    if method == 'mean':
+        return local['mean'].values, None, None
+    if method == 'median':
+        return local['median'].values, None, None
+    if method == 'skewness':
+        return (local['median'].values, local['mean'].values,
+                local['skewness'].values)
+    return vline_perc['rperc'].values, vline_perc['lperc'].values, None
+
+
+def detect(grids, obs_file, rad=0, method='mean', prob=0.95, skewness=None,
+           percentile=None, flag=True, save=False, outfile=None, header=True,
+           optional_stats=None):
+    """Detect and correct irregularities of one candidate station.
+
+    Same contract as the reference (homog.py:27-276): an observation is
+    flagged when it lies outside the interval of probability ``prob`` centred
+    in the local PDF (quantiles ``(1-prob)/2`` and ``1-(1-prob)/2`` of the
+    simulated values at the station's node, both ends inclusive); flagged
+    values are replaced by the local mean, median, the skewness-selected one
+    of the two, or the nearest bound of the ``percentile`` interval.  Missing
+    observations (``nodata`` or absent years) are first filled with the local
+    mean and then tested like the others.
+
+    Returns ``(homogenised PointSet, detected_number, missing_data)``; the
+    PointSet has the candidate's columns, ``clim`` corrected, a ``Flag``
+    column (observed value where corrected, ``nodata`` elsewhere) and the
+    requested optional statistics.
+    """
+    sel = _select_stats(method, skewness, optional_stats)
+    obs, obs_xy, nodatas = _prepare_obs(obs_file, grids, header)
+    local = grids.stats_area(obs_xy, rad, p=prob, save=save, **sel).values
+
+    meanvalues = local['mean'].values
+    fn = 0
+    if obs.values.shape[0] < grids.dz:
+        obs, fn = fill_station(obs, meanvalues, grids.zi, grids.zi + grids.dz,
+                               grids.cellz, header)
+    if method == 'percentile' and percentile != prob:
+        grids.reset_read()
+        vline_perc = grids.stats_area(obs_xy, rad, lperc=True, p=percentile,
+                                      save=False).values
+    else:
+        vline_perc = local
+    fix_a, fix_b, fix_c = _fix_columns(method, local, vline_perc)
+    clim = obs.values['clim'].values.astype(np.float64)
+    as2d = lambda a: None if a is None else np.asarray(a, np.float64)[None, :]
+    filled, homog, flagcol, det = _capi.detect(
+        as2d(clim), as2d(meanvalues), as2d(local['lperc'].values),
+        as2d(local['rperc'].values), as2d(fix_a), as2d(fix_b), as2d(fix_c),
+        method=method, thr=float(skewness or 0.0), nodata=obs.nodata,
+        device=grids.device)
+    homogenised, detected_number = _finish(
+        obs, local, None, method, skewness,
+        (filled[0], homog[0], flagcol[0], det[0]), flag, optional_stats, grids,
+        obs_xy, rad)
+    if save and outfile:
+        homogenised.save(outfile, header)
+    return homogenised, detected_number, fn + nodatas
+
+
+def detect_many(grids, obs_list, rad=0, method='mean', prob=0.95,
+                skewness=None, percentile=None, flag=True, header=True,
+                optional_stats=None):
+    """Extension: ``detect`` for many candidate stations against ONE stack
+    (the ``interface/simstats.py:204-209`` calling pattern) with one K2c and
+    one K3 launch.  Returns a list of ``detect``-style tuples."""
+    sel = _select_stats(method, skewness, optional_stats)
+    prepared = [_prepare_obs(o, grids, header) for o in obs_list]
+    locs = [p[1] for p in prepared]
+    locals_ = [ps.values for ps in
+               grids.stats_area_many(locs, rad, p=prob, **sel)]
+    if method == 'percentile' and percentile != prob:
+        vperc = [ps.values for ps in
+                 grids.stats_area_many(locs, rad, lperc=True, p=percentile)]
+    else:
+        vperc = locals_
+    S, dz = len(prepared), grids.dz
+    cols = [np.empty((S, dz)) for _ in range(7)]
+    fns, obs_filled = [], []
+    for s, (obs, _, _) in enumerate(prepared):
+        local = locals_[s]
+        fn = 0
+        if obs.values.shape[0] < dz:
+            obs, fn = fill_station(obs, local['mean'].values, grids.zi,
+                                   grids.zi + grids.dz, grids.cellz, header)
+        fns.append(fn)
+        obs_filled.append(obs)
+        fa, fb, fc = _fix_columns(method, local, vperc[s])
+        cols[0][s] = obs.values['clim'].values
+        cols[1][s] = local['mean'].values
+        cols[2][s] = local['lperc'].values
+        cols[3][s] = local['rperc'].values
+        cols[4][s] = fa
+        cols[5][s] = fa if fb is None else fb
+        cols[6][s] = fa if fc is None else fc
+    filled, homog, flagcol, det = _capi.detect(
+        *cols, method=method, thr=float(skewness or 0.0),
+        nodata=prepared[0][0].nodata if prepared else -999.9,
+        device=grids.device)
+    out = []
+    for s, obs in enumerate(obs_filled):
+        hom, dn = _finish(obs, locals_[s], None, method, skewness,
+                          (filled[s], homog[s], flagcol[s], det[s]), flag,
+                          optional_stats, grids, locs[s], rad)
+        out.append((hom, dn, fns[s] + prepared[s][2]))
+    return out
+
+
+def fill_station(pset_file, values, time_min, time_max, time_step=1,
+                 header=True):
+    """Expand an incomplete station series to every time step of the grid,
+    filling the synthesised rows with ``values`` (homog.py:279-337).
+
+    Rows are matched to ``arange(time_min, time_max, time_step)`` by a merge
+    walk; a synthesised row copies x, y and the columns between ``time`` and
+    ``clim`` (the station id) from the first row.  Returns ``(PointSet,
+    number of rows added)``.
+    """
+    if isinstance(pset_file, gr.PointSet):
+        pset = pset_file
+    else:
+        pset = gr.PointSet()
+        pset.load(pset_file, header=header)
+    frame = pset.values
+    varcol = pset.varnames.index('clim')
+    times = np.arange(time_min, time_max, time_step)
+    have = frame['time'].values
+    first = frame.iloc[0].values
+    filled = np.zeros((times.shape[0], frame.shape[1]))
+    j = 0
+    added = 0
+    for i, t in enumerate(times):
+        if j < have.shape[0] and t == have[j]:
+            filled[i] = frame.iloc[j].values
+            j += 1
+        else:
+            row = np.concatenate([first[:2], [t], first[3:varcol],
+                                  [values[i]]])
+            filled[i] = row[:frame.shape[1]]
+            added += 1
+    pset.values = pd.DataFrame(filled, columns=frame.columns)
+    return pset, added
+
+
+def list_stations(pset_file, header=True, variables=None):
+    """Station ids present in a point-set (homog.py:340-380)."""
+    pset = gr.loadcheck(pset_file, header)
+    ids = pset.values['station'].unique()
+    return [int(i) for i in ids]
+
+
+def take_candidate(pset_file, station, header=True, save=False, path=None):
+    """Split a network point-set into the candidate station and its
+    references, dropping Flag and optional-statistics columns
+    (homog.py:442-504)."""
+    pset = gr.loadcheck(pset_file, header)
+    is_cand = pset.values['station'] == int(station)
+    drop = ['Flag', 'mean', 'median', 'std', 'pdet', 'variance', 'coefvar',
+            'skewness']
+    cand = pset.values[is_cand].drop(drop, axis=1, errors='ignore')
+    refs = pset.values[~is_cand].drop(drop, axis=1, errors='ignore')
+    names = list(cand.columns)
+    cand_pset = gr.PointSet('Candidate_' + str(station), pset.nodata,
+                            len(names), list(names), cand)
+    refs_pset = gr.PointSet('References_' + str(station), pset.nodata,
+                            len(names), list(names), refs)
+    if save and path:
+        import os
+        base, ext = os.path.splitext(path)
+        cand_pset.save(base + '_candidate' + ext, header)
+        refs_pset.save(base + '_neighbours' + ext, header)
+    return cand_pset, refs_pset
+
+
+def update_station(stations_pset, station, header=True):
+    """Write a homogenised station back into the network point-set, adding
+    any new columns as NaN first (homog.py:507-545; index-aligned, like
+    ``DataFrame.update``)."""
+    pset = gr.loadcheck(stations_pset, header)
+    if sorted(pset.varnames) != sorted(station.varnames):
+        for var in [v for v in station.varnames if v not in pset.varnames]:
+            pset.add_var(np.repeat(np.nan, pset.values.shape[0]), var)
+    pset.values.update(station.values)
+    return pset

@@ -1,0 +1,432 @@
+# -*- coding: utf-8 -*-
+"""GPU parity: the CUDA path (through the C ABI) against the CPU oracle.
+
+Bit-exact: order statistics (median, percentiles, mode), detection flags,
+counts and node indexing.  <= 1e-5 relative (absolute floor for skewness near
+0): moments on the full-grid float32 maps.  Station tables are float64 and
+agree with the oracle to summation-order noise (1e-12 relative).
+"""
+import os
+
+import numpy as np
+import pandas as pd
+import pytest
+
+from conftest import GOLDEN_CASES, load_golden
+
+pytestmark = pytest.mark.gpu
+
+from gsimcli_b200 import _capi, synth                     # noqa: E402
+from gsimcli_b200.tools import grid as gr, homog as hmg   # noqa: E402
+from oracle import np_oracle as O                         # noqa: E402
+
+ND = -999.9
+ALLF = (_capi.MEAN | _capi.MEDIAN | _capi.SKEW | _capi.VAR | _capi.STD
+        | _capi.COEFVAR | _capi.PERC)
+QS = [round(0.05 * k, 2) for k in range(1, 20)]
+
+
+def f32(x):
+    return np.asarray(x, dtype=np.float64).astype(np.float32)
+
+
+def same_bits(a, b):
+    a, b = f32(a), f32(b)
+    assert a.shape == b.shape
+    ok = (a == b) | (np.isnan(a) & np.isnan(b))
+    assert ok.all(), 'first mismatch at {0}: {1} vs {2}'.format(
+        np.argwhere(~ok)[0], a[~ok][0], b[~ok][0])
+
+
+def close(a, b, rtol=1e-5, atol=0.0):
+    a, b = np.asarray(a, float), np.asarray(b, float)
+    assert np.array_equal(np.isnan(a), np.isnan(b))
+    np.testing.assert_allclose(a, b, rtol=rtol, atol=atol, equal_nan=True)
+
+
+def check_grid(st, p=0.95, percentiles=QS, mode=True, n0=0, nn=None):
+    """Full-grid planes of the CUDA path vs the oracle on the same f32 values."""
+    st = np.ascontiguousarray(st, dtype=np.float32)
+    R, N = st.shape
+    nn = N - n0 if nn is None else nn
+    stack = _capi.Stack(R, N)
+    stack.upload(st)
+    flags = ALLF | (_capi.MODE if mode else 0)
+    out = stack.stats_grid(flags, p, percentiles, ND, n0, nn)
+    stack.close()
+    ref = O.grid_stats(st[:, n0:n0 + nn], ND, flags, p, percentiles)
+    sigma = np.nanmax(ref['stdmap']) if np.isfinite(ref['stdmap']).any() else 1.0
+    close(out[0], ref['meanmap'])
+    same_bits(out[1], ref['medianmap'])
+    close(out[2], ref['skewmap'], rtol=1e-4, atol=2e-4)
+    close(out[3], ref['varmap'], atol=1e-5 * sigma ** 2 * 1e-3)
+    close(out[4], ref['stdmap'], atol=1e-6 * sigma)
+    close(out[5], ref['coefvarmap'], atol=1e-6)
+    same_bits(out[6], ref['percmap'][:, 0])
+    same_bits(out[7], ref['percmap'][:, 1])
+    k = 8
+    if percentiles:
+        for i in range(len(percentiles)):
+            same_bits(out[k + i], ref['percentiles'][:, i])
+        k += len(percentiles)
+    if mode:
+        same_bits(out[k], ref['modemap'])
+
+
+def test_device_is_blackwell():
+    info = _capi.device_info(0)
+    assert info['cc'][0] >= 10, info
+
+
+def test_synth_device_equals_numpy():
+    dims = [37, 11, 5]
+    N = int(np.prod(dims))
+    for node0, n in ((0, N), (100, 777)):
+        stack = _capi.Stack(9, n)
+        stack.synth_fill(1234, dims, node0, ND)
+        got = stack.download()
+        stack.close()
+        exp = synth.stack(1234, 9, dims, node0, node0 + n, ND)
+        assert np.array_equal(got, exp)
+
+
+def test_upload_download_roundtrip():
+    rng = np.random.default_rng(0)
+    a = rng.normal(size=(7, 333)).astype(np.float32)
+    stack = _capi.Stack(7, 333)
+    stack.upload(a)
+    assert np.array_equal(stack.download(), a)
+    assert np.array_equal(stack.download(2, 3, 10, 100), a[2:5, 10:110])
+    stack.close()
+
+
+@pytest.mark.parametrize('name', GOLDEN_CASES)
+def test_grid_stats_golden_stacks(name):
+    g = load_golden(name)
+    st = f32(g['stack'])
+    st[np.array(g['stack']) == g['nodata']] = np.float32(g['nodata'])
+    check_grid(st)
+    # and against the reference's own float64 results at float32 resolution
+    stack = _capi.Stack(*st.shape)
+    stack.upload(st)
+    for rec in g['stats']:
+        out = stack.stats_grid(ALLF, rec['p'], None, g['nodata'])
+        n = st.shape[1] - g['header']
+        close(out[0][:n], np.array(rec['maps']['meanmap'])[:n], rtol=2e-6)
+        close(out[1][:n], np.array(rec['maps']['medianmap'])[:n], rtol=2e-7)
+        close(out[6][:n], np.array(rec['maps']['percmap'])[:n, 0], rtol=2e-7)
+    stack.close()
+
+
+@pytest.mark.parametrize('R', [1, 2, 3, 5, 31, 32, 33, 50, 64, 65, 100, 128,
+                               200, 255, 256, 500, 512, 513, 1000, 1024])
+def test_grid_stats_all_R(R):
+    dims = [13, 7, 5]            # N = 455: not a multiple of 32
+    st = synth.stack(1000 + R, R, dims)
+    st[:, 3] = 812.5             # constant column
+    st[:, 4] = np.float32(ND)    # all nodata
+    st[:, 5] = np.float32(ND)
+    st[R // 2, 5] = 640.25       # n == 1
+    if R >= 2:
+        st[:, 6] = np.float32(ND)
+        st[0, 6], st[R - 1, 6] = 7.5, 8.5   # n == 2
+    st[:, 8] = np.where(np.arange(R) % 2 == 0, 500.0, 600.0)   # two atoms
+    check_grid(st)
+
+
+def test_grid_stats_subrange_and_no_mode():
+    st = synth.stack(5, 200, [20, 10, 4])
+    check_grid(st, p=0.9, percentiles=[0.0, 0.5, 1.0, 0.333], mode=False,
+               n0=37, nn=401)
+    check_grid(st, percentiles=None, mode=True, n0=64, nn=64)
+
+
+def test_grid_stats_arbitrary_decimals():
+    rng = np.random.default_rng(3)
+    st = np.round(rng.gamma(2.0, 150.0, size=(200, 700)) + 300.0, 4)
+    st[rng.uniform(size=st.shape) < 0.01] = ND
+    check_grid(st.astype(np.float32))
+    # NaN in the data is dropped like nodata
+    st32 = st.astype(np.float32)
+    st32[5, 10] = np.nan
+    ref = st32.copy()
+    ref[5, 10] = np.float32(ND)
+    s1 = _capi.Stack(*st32.shape)
+    s1.upload(st32)
+    a = s1.stats_grid(ALLF, 0.95, None, ND)
+    s1.upload(ref)
+    b = s1.stats_grid(ALLF, 0.95, None, ND)
+    s1.close()
+    assert np.array_equal(a, b, equal_nan=True)
+
+
+def test_moments_only_kernel():
+    flags = _capi.MEAN | _capi.SKEW | _capi.VAR | _capi.STD | _capi.COEFVAR
+    for R in (1, 2, 7, 16, 17, 50, 200, 1000, 1500):
+        st = synth.stack(77, R, [19, 6, 4])
+        st[:, 3] = 812.5
+        st[:, 4] = np.float32(ND)
+        stack = _capi.Stack(*st.shape)
+        stack.upload(st)
+        out = stack.stats_grid(flags, 0.95, None, ND)
+        stack.close()
+        ref = O.grid_stats(st, ND, flags)
+        sigma = 150.0
+        close(out[0], ref['meanmap'])
+        close(out[1], ref['skewmap'], rtol=1e-4, atol=2e-4)
+        close(out[2], ref['varmap'], atol=1e-8 * sigma ** 2)
+        close(out[3], ref['stdmap'], atol=1e-6 * sigma)
+        close(out[4], ref['coefvarmap'], atol=1e-6)
+
+
+def test_mode_heavy_ties():
+    rng = np.random.default_rng(11)
+    for R in (64, 200, 1000):
+        st = rng.integers(0, 6, size=(R, 96)).astype(np.float32) * 0.25 + 500
+        st[:, 0] = 7.0
+        st[rng.uniform(size=st.shape) < 0.02] = np.float32(ND)
+        check_grid(st, percentiles=[0.25, 0.75])
+
+
+@pytest.mark.parametrize('name', ['kat_appendix_c', 'dyadic_even',
+                                  'dyadic_odd', 'decimals_lf'])
+def test_stats_area_golden(name):
+    g = load_golden(name)
+    st = f32(g['stack'])
+    grids = gr.GridFiles.from_array(st, g['dims'], g['first_coord'],
+                                    g['cells_size'], g['nodata'])
+    exact = name != 'decimals_lf'
+    for rec in g['stats_area']:
+        ps = grids.stats_area(rec['loc'], tol=rec['tol'], lmean=True,
+                              lmed=True, lskew=True, lvar=True, lstd=True,
+                              lcoefvar=True, lperc=True, p=rec['p'])
+        assert ps.name == rec['name']
+        assert list(ps.values.columns) == rec['table']['columns']
+        ref = np.array(rec['table']['values'])
+        got = ps.values.values
+        if exact:       # dyadic inputs: f32 storage is lossless
+            close(got, ref, rtol=1e-12, atol=1e-9)
+            for col in ('x', 'y', 'z', 'median', 'lperc', 'rperc'):
+                j = rec['table']['columns'].index(col)
+                assert np.array_equal(got[:, j], ref[:, j], equal_nan=True)
+        else:           # contract B: reference arithmetic on f32-rounded inputs
+            _, tab = O.stats_area(st, g['dims'], g['first_coord'],
+                                  g['cells_size'], g['nodata'], rec['loc'],
+                                  rec['tol'], O.FLAG_MEAN | O.FLAG_MED
+                                  | O.FLAG_SKEW | O.FLAG_VAR | O.FLAG_STD
+                                  | O.FLAG_COEFVAR | O.FLAG_PERC, rec['p'])
+            close(got, tab.values, rtol=1e-12, atol=1e-9)
+            for col in ('median', 'lperc', 'rperc'):
+                j = rec['table']['columns'].index(col)
+                assert np.array_equal(got[:, j], tab.values[:, j],
+                                      equal_nan=True)
+    grids.dump()
+
+
+@pytest.mark.parametrize('name', ['kat_appendix_c', 'dyadic_even',
+                                  'dyadic_odd'])
+def test_detect_golden(name):
+    g = load_golden(name)
+    st = f32(g['stack'])
+    grids = gr.GridFiles.from_array(st, g['dims'], g['first_coord'],
+                                    g['cells_size'], g['nodata'])
+    for rec in g['detect']:
+        df = pd.DataFrame(np.array(rec['obs'], float),
+                          columns=['x', 'y', 'time', 'station', 'clim'])
+        ps = gr.PointSet('cand', g['nodata'], 5, list(df.columns), df)
+        hom, dn, md = hmg.detect(grids, ps, **rec['kwargs'])
+        assert hom.name == rec['name']
+        assert dn == rec['detected_number'] and md == rec['missing_data']
+        ref = pd.DataFrame(np.array(rec['homogenised']['values']),
+                           columns=rec['homogenised']['columns'])
+        assert sorted(hom.values.columns) == sorted(ref.columns)
+        for col in ref.columns:
+            close(hom.values[col].values, ref[col].values, rtol=1e-12,
+                  atol=1e-9)
+        assert np.array_equal(hom.values['Flag'].values, ref['Flag'].values)
+    grids.dump()
+
+
+def test_detect_many_matches_oracle_config2_shape():
+    """BASELINE config 2 shape, scaled down in nodes: 200 realizations, 20
+    stations, detection + median correction."""
+    dims, first, cells = [30, 24, 60], [1000.0, 2000.0, 1950], [50.0, 50.0, 1]
+    R = 200
+    grids = gr.GridFiles.from_synthetic(1002, R, dims, first, cells, ND)
+    host = synth.stack(1002, R, dims)
+    sts = synth.stations(1002, 20, R, dims, first, cells, tol=1)
+    for method, kw in (('median', {}), ('mean', {}),
+                       ('skewness', dict(skewness=0.4)),
+                       ('percentile', dict(percentile=0.8))):
+        obs = [gr.PointSet('c%d' % i, ND, 5,
+                           ['x', 'y', 'time', 'station', 'clim'],
+                           pd.DataFrame(s['obs'], columns=['x', 'y', 'time',
+                                                           'station', 'clim']))
+               for i, s in enumerate(sts)]
+        res = hmg.detect_many(grids, obs, rad=1, method=method, prob=0.95,
+                              **kw)
+        total = 0
+        for s, (hom, dn, md) in zip(sts, res):
+            df = pd.DataFrame(s['obs'], columns=['x', 'y', 'time', 'station',
+                                                 'clim'])
+            ohom, odn, omd = O.detect(host, dims, first, cells, ND, df, ND,
+                                      rad=1, method=method, prob=0.95, **kw)
+            assert (dn, md) == (odn, omd)
+            assert np.array_equal(hom.values['Flag'].values,
+                                  ohom['Flag'].values)
+            close(hom.values['clim'].values, ohom['clim'].values, rtol=1e-12)
+            total += dn
+        assert total > 0
+    # single-station API gives the same as the batch
+    df = pd.DataFrame(sts[0]['obs'], columns=['x', 'y', 'time', 'station',
+                                              'clim'])
+    ps = gr.PointSet('c0', ND, 5, list(df.columns), df)
+    hom, dn, md = hmg.detect(grids, ps, rad=1, method='median', prob=0.95)
+    ohom, odn, omd = O.detect(host, dims, first, cells, ND, df, ND, rad=1,
+                              method='median', prob=0.95)
+    assert (dn, md) == (odn, omd)
+    assert np.array_equal(hom.values['Flag'].values, ohom['Flag'].values)
+    grids.dump()
+
+
+def test_stats_area_large_disc_uses_global_sort():
+    dims, first, cells = [40, 40, 3], [0.0, 0.0, 0], [1.0, 1.0, 1]
+    R = 1000
+    grids = gr.GridFiles.from_synthetic(9, R, dims, first, cells, ND)
+    host = synth.stack(9, R, dims)
+    for tol in (0, 3, 4):          # K = 1, 29, 49 -> 49000 values per layer
+        ps = grids.stats_area([20.2, 19.7], tol=tol, lmean=True, lmed=True,
+                              lvar=True, lperc=True, lskew=True, lmode=True)
+        _, tab = O.stats_area(host, dims, first, cells, ND, [20.2, 19.7], tol,
+                              O.FLAG_MEAN | O.FLAG_MED | O.FLAG_VAR
+                              | O.FLAG_PERC | O.FLAG_SKEW)
+        got = ps.values
+        for col in tab.columns:
+            close(got[col].values, tab[col].values, rtol=1e-11, atol=1e-9)
+        for col in ('median', 'lperc', 'rperc'):
+            assert np.array_equal(got[col].values, tab[col].values)
+    grids.dump()
+
+
+def _py_float32(lines):
+    return np.array([np.float32(float(s)) for s in lines], dtype=np.float32)
+
+
+def test_decode_text_forms(tmp_path):
+    rng = np.random.default_rng(5)
+    vals = np.round(rng.gamma(2.0, 150.0, size=4000) + 300.0, 4)
+    vals[::97] = ND
+    N = vals.size
+    # fixed width CRLF, 14 bytes per node
+    text = synth.to_text(vals, '%12.4f', '\r\n')
+    assert len(text) == 14 * N
+    stack = _capi.Stack(3, N)
+    stack.decode_text(0, text, 0, 14)
+    # LF, variable width, 3 header lines
+    text2 = synth.to_text(vals, '%.4f', '\n', ['name', '1', 'var'])
+    stack.decode_text(1, text2, 3, 0)
+    # %-10.6f (GridArr.save format) and no trailing newline
+    text3 = synth.to_text(vals, '%-10.6f', '\n')[:-1]
+    stack.decode_text(2, text3, 0, 0)
+    got = stack.download()
+    exp = _py_float32(['%.4f' % v for v in vals])
+    for r in range(3):
+        assert np.array_equal(got[r], exp), r
+    # node-sharded decode: lines [1000, 1500) into nodes [0, 500)
+    s2 = _capi.Stack(2, 500)
+    s2.decode_text(0, text, 0, 14, 1000, 0, 500)
+    s2.decode_text(1, text2, 3, 0, 1000, 0, 500)
+    g2 = s2.download()
+    assert np.array_equal(g2[0], exp[1000:1500])
+    assert np.array_equal(g2[1], exp[1000:1500])
+    s2.close()
+    stack.close()
+
+
+def test_decode_number_syntax():
+    lines = ['1', '-1', '+2.5', '.5', '5.', '1e3', '1E-3', '-1.5e+2', '  7  ',
+             '\t8\r', '0', '-0.0', '000123.4500', '1234567890123456',
+             '0.1', '0.30000000000000004', '8.5e22', '1e-5', '123456789.123456789',
+             '3.4028235e38', '1e39', '1e-46', 'inf', '-Infinity', 'nan',
+             '812.34559999999999', '9007199254740993', '0.000001', '1.17549435e-38',
+             '4.9406564584124654e-20', '16777217', '16777219', '0.50000000000000011']
+    text = ('\n'.join(lines) + '\n').encode()
+    stack = _capi.Stack(1, len(lines))
+    stack.decode_text(0, text, 0, 0)
+    got = stack.download()[0]
+    stack.close()
+    with np.errstate(over='ignore'):
+        exp = _py_float32(lines)
+    ok = (got == exp) | (np.isnan(got) & np.isnan(exp))
+    assert ok.all(), [(lines[i], got[i], exp[i]) for i in np.flatnonzero(~ok)]
+    assert np.signbit(got[lines.index('-0.0')])
+
+
+@pytest.mark.parametrize('bad', ['abc', '1.2.3', '', '1e', '--1', '1 2',
+                                 '0x10', '1,5'])
+def test_decode_malformed_line_raises_valueerror(bad):
+    text = ('1.0\n2.0\n' + bad + '\n4.0\n').encode()
+    stack = _capi.Stack(1, 4)
+    with pytest.raises(ValueError):
+        stack.decode_text(0, text, 0, 0)
+    stack.close()
+    fixed = ('%12s\r\n' * 4 % ('1.0', '2.0', bad[:12], '4.0')).encode()
+    stack = _capi.Stack(1, 4)
+    with pytest.raises(ValueError):
+        stack.decode_text(0, fixed, 0, 14)
+    stack.close()
+
+
+def test_gridfiles_load_from_files_matches_from_array(tmp_path):
+    dims, first, cells = [9, 8, 6], [1000.0, 5000.0, 1990], [100.0, 50.0, 1]
+    R = 12
+    st = synth.stack(21, R, dims)
+    sel = dict(lmean=True, lmed=True, lskew=True, lvar=True, lstd=True,
+               lcoefvar=True, lperc=True)
+    ref = gr.GridFiles.from_array(st, dims, first, cells, ND)
+    exp = ref.stats(p=0.9, **sel)
+    for fmt, eol, hdr in (('%12.4f', '\r\n', 0), ('%.4f', '\n', 3),
+                          ('%12.4f', '\r\n', 3)):
+        d = tmp_path / ('f%d%d' % (len(eol), hdr))
+        d.mkdir()
+        header = ['sim', '1', 'v'] if hdr else None
+        firstfile = synth.write_stack(str(d), 'x_sim', st, fmt, eol, header)
+        g = gr.GridFiles()
+        g.load(firstfile, R, dims, first, cells, ND, hdr)
+        assert g.nfiles == R and g.cells == 432
+        got = g.stats(p=0.9, **sel)
+        assert sorted(got) == sorted(exp)
+        for k in exp:
+            assert np.array_equal(got[k].val, exp[k].val, equal_nan=True), k
+        # stats_area works with header > 0 here
+        a = g.stats_area([1350.0, 5160.0], tol=1, lmean=True, lperc=True)
+        b = ref.stats_area([1350.0, 5160.0], tol=1, lmean=True, lperc=True)
+        assert np.array_equal(a.values.values, b.values.values)
+        # open_files with an explicit list
+        g2 = gr.GridFiles()
+        g2.open_files(list(g.files), dims, first, cells, ND, hdr)
+        assert np.array_equal(g2.stats(lmed=True)['medianmap'].val,
+                              exp['medianmap'].val, equal_nan=True)
+        g2.purge()
+        assert not os.path.exists(firstfile)
+        g.dump()
+    with pytest.raises(IOError):
+        gr.GridFiles().load(str(tmp_path / 'nope_sim.out'), 3, dims, first,
+                            cells, ND, 0)
+    ref.dump()
+
+
+def test_save_extraction_at_station(tmp_path):
+    dims, first, cells = [6, 5, 3], [0.0, 0.0, 2000], [10.0, 10.0, 1]
+    st = synth.stack(4, 7, dims)
+    firstfile = synth.write_stack(str(tmp_path), 's_sim', st)
+    g = gr.GridFiles()
+    g.load(firstfile, 7, dims, first, cells, ND, 0)
+    g.stats_area([20.0, 30.0], tol=0, lmean=True, save=True)
+    ps = gr.PointSet(psetpath=str(tmp_path / 'sim values at (3, 4, 2001).prn'))
+    assert ps.name == 'realisations at location (3, 4, 2001)'
+    node = 2 + 6 * 3 + 30 * 1
+    col = st[:, node].astype(float)
+    col[st[:, node] == np.float32(ND)] = np.nan
+    assert np.allclose(ps.values['value'].values, col, equal_nan=True)
+    g.dump()
