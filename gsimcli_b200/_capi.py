@@ -165,9 +165,9 @@ class Stack(object):
         self.pitch = pitch.value
 
     def close(self):
-        if getattr(self, 'handle', None):
-            lib().gsb_stack_destroy(self.handle)
-            self.handle = None
+        if getattr(self, 'handle', None) and _lib is not None:
+            _lib.gsb_stack_destroy(self.handle)
+        self.handle = None
 
     __del__ = close
 

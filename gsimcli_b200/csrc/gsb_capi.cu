@@ -102,13 +102,13 @@ static int make_tmap(gsb_stack* s) {
     }
     const cuuint64_t dims[2] = {(cuuint64_t)s->N, (cuuint64_t)s->R};
     const cuuint64_t strides[1] = {(cuuint64_t)s->pitch * 4};
-    const cuuint32_t box[2] = {32, 32};
+    const cuuint32_t box[2] = {32, (cuuint32_t)gsb_k2_box_rows(s->R)};
     const cuuint32_t estr[2] = {1, 1};
     CUresult r = ((encode_tiled_fn)fn)(&s->tmap_k2, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, s->data,
                                        dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                                        CU_TENSOR_MAP_SWIZZLE_128B,
                                        CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
-                                       CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                                       CU_TENSOR_MAP_FLOAT_OOB_FILL_NAN_REQUEST_ZERO_FMA);
     if (r != CUDA_SUCCESS) {
         gsb_set_error("cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
         return GSB_ECUDA;

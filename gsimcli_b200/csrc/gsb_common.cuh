@@ -50,7 +50,8 @@ struct gsb_stack {
     void* pinned;
     size_t pinned_bytes;
     cudaEvent_t ev0, ev1;
-    CUtensorMap tmap_k2;   // 2-D map (node, realization), box 32 x 32, 128B swizzle
+    CUtensorMap tmap_k2;   // 2-D map (node, realization): box 32 nodes x
+                           // gsb_k2_box_rows(R) rows, 128B swizzle, OOB -> NaN
     int tmap_ok;
 };
 
@@ -81,6 +82,8 @@ struct GsbPlanes {
 // does not fit
 int gsb_build_planes(uint32_t flags, double p, const double* q, int nq,
                      GsbPlanes* out);
+
+int gsb_k2_box_rows(int64_t R);   // rows per TMA box of the K2 tile (k2_grid_sort.cu)
 
 // ---------------------------------------------------------------- launchers
 int gsb_launch_k2_sort(gsb_stack* s, const GsbPlanes& pl, float nodata,

@@ -26,6 +26,7 @@
 // HBM traffic: the stack is read exactly once (4 B per node-realization).
 #include "gsb_common.cuh"
 #include <utility>
+#include <stdlib.h>
 
 namespace {
 
@@ -39,11 +40,13 @@ struct K2Args {
     int R;
     int nchunks;
     int nplanes;
+    int lockstep;      // experiment knob: block barriers inside the sort (GSB_K2_LOCKSTEP)
     float nodata;
     long long ntiles;
-    long long n0;
-    long long nn;
-    float* out;
+    long long n0;      // first column of tile 0 (multiple of 4: TMA needs 16-byte aligned boxes)
+    long long nn;      // columns from n0 to the end of the requested range
+    long long skip;    // leading columns of tile 0 that precede the requested range
+    float* out;        // plane 0, column n0 (may point `skip` elements before the buffer)
     long long out_pitch;
     unsigned char kind[GSB_MAX_PLANES];
     double q[GSB_MAX_PLANES];
@@ -90,16 +93,38 @@ __device__ __forceinline__ void ce4(float (&v)[4][IPT]) {
     }
 }
 
+// All 8 warps execute the same straight-line sorting code (~250 KB of SASS
+// per tile at IPT = 32).  Left alone they drift apart and each streams the
+// code through the instruction caches on its own: ncu showed `no_instruction`
+// as the top stall (2.9 per issue).  A block barrier every few hundred
+// instructions keeps the warps inside one I-cache window, so a line is
+// fetched once per SM instead of once per warp.
+__device__ __forceinline__ void lockstep() { __syncthreads(); }
+
+template <int I>
+__device__ __forceinline__ void lockstep_every(bool on) {
+    if constexpr ((I % 48) == 47) { if (on) lockstep(); }
+}
+
 template <int IPT, int... Is>
-__device__ __forceinline__ void oem_apply(float (&v)[4][IPT],
+__device__ __forceinline__ void oem_apply(float (&v)[4][IPT], bool ls,
                                           std::integer_sequence<int, Is...>) {
-    (ce4<Oem<IPT>::net.a[Is], Oem<IPT>::net.b[Is], IPT>(v), ...);
+    ((ce4<Oem<IPT>::net.a[Is], Oem<IPT>::net.b[Is], IPT>(v), lockstep_every<Is>(ls)), ...);
 }
 
 template <int IPT>
-__device__ __forceinline__ void sort_in_lane(float (&v)[4][IPT]) {
+__device__ __forceinline__ void sort_in_lane(float (&v)[4][IPT], bool ls) {
     if constexpr (IPT > 1)
-        oem_apply<IPT>(v, std::make_integer_sequence<int, Oem<IPT>::net.n>{});
+        oem_apply<IPT>(v, ls, std::make_integer_sequence<int, Oem<IPT>::net.n>{});
+}
+
+// v *= f with f = +-1.  Inline PTX keeps it an FMUL (fma pipe, idle here):
+// NVVM would rewrite v * select(-1, 1) into FSEL(v, -v) on the alu pipe, which
+// is the pipe the FMNMX compare-exchanges saturate.
+__device__ __forceinline__ float mul_sign(float x, float f) {
+    float r;
+    asm("mul.f32 %0, %1, %2;" : "=f"(r) : "f"(x), "f"(f));
+    return r;
 }
 
 template <int IPT>
@@ -107,8 +132,10 @@ __device__ __forceinline__ void scale_all(float (&v)[4][IPT], float f) {
 #pragma unroll
     for (int c = 0; c < 4; ++c)
 #pragma unroll
-        for (int j = 0; j < IPT; ++j) v[c][j] *= f;
+        for (int j = 0; j < IPT; ++j) v[c][j] = mul_sign(v[c][j], f);
 }
+
+
 
 // Bitonic merge phases across the warp.  Logical position = lane*IPT + reg.
 // On entry every lane is sorted ascending in ITS stored values, and lanes with
@@ -116,7 +143,7 @@ __device__ __forceinline__ void scale_all(float (&v)[4][IPT], float f) {
 // lane's sign state.  On exit all lanes hold plain x, globally ascending.
 template <int IPT>
 __device__ __forceinline__ void merge_across_lanes(float (&v)[4][IPT], int lane,
-                                                   bool neg) {
+                                                   bool neg, bool ls_on) {
 #pragma unroll
     for (int L = 2; L <= 32; L <<= 1) {
         const bool desc = (L < 32) && ((lane & L) != 0);
@@ -133,6 +160,7 @@ __device__ __forceinline__ void merge_across_lanes(float (&v)[4][IPT], int lane,
                     const float o = __shfl_xor_sync(FULL, v[c][j], ls);
                     v[c][j] = fminf(v[c][j], -o);
                 }
+            if constexpr (IPT >= 8) { if (ls_on) lockstep(); }
         }
         if constexpr (IPT > 1) {
             scale_all<IPT>(v, (desc != neg) ? -1.0f : 1.0f);
@@ -149,6 +177,7 @@ __device__ __forceinline__ void merge_across_lanes(float (&v)[4][IPT], int lane,
                             v[c][j | s] = fmaxf(x, y);
                         }
                     }
+            if constexpr (IPT >= 8) { if (ls_on) lockstep(); }
         } else {
             scale_all<IPT>(v, (desc != neg) ? -1.0f : 1.0f);
             neg = desc;
@@ -183,52 +212,87 @@ __device__ __forceinline__ int scr_addr(int p) {
     return l * IPT + ((j + ((l * IPT) >> 5)) & (IPT - 1));
 }
 
+// nodata / NaN / out-of-bounds (TMA fills those with NaN) -> +INF, everything
+// carrying the lane's initial sign.  setp.ne is the ORDERED not-equal: false
+// for NaN, so one compare covers bn.replace(arr, nodata, nan) (grid.py:681)
+// and NaN dropping.
+__device__ __forceinline__ float sanitize(float x, float nodata, float sg, float infs) {
+    float r;
+    const float xs = mul_sign(x, sg);
+    asm("{\n.reg .pred p;\nsetp.ne.f32 p, %1, %2;\nselp.f32 %0, %3, %4, p;\n}"
+        : "=f"(r) : "f"(x), "f"(nodata), "f"(xs), "f"(infs));
+    return r;
+}
+__device__ __forceinline__ bool is_valid(float x, float nodata) {
+    int r;
+    asm("{\n.reg .pred p;\nsetp.ne.f32 p, %1, %2;\nselp.s32 %0, 1, 0, p;\n}"
+        : "=r"(r) : "f"(x), "f"(nodata));
+    return r != 0;
+}
+
+template <int IPT>
+__device__ __forceinline__ void dump_column(float* scr, const float (&col)[IPT], int lane) {
+#pragma unroll
+    for (int j = 0; j < IPT; ++j)
+        scr[lane * IPT + ((j + ((lane * IPT) >> 5)) & (IPT - 1))] = col[j];
+}
+
+// bit j of lane l: sorted[p] == sorted[p-1], p = l*IPT + j
+template <int IPT>
+__device__ __forceinline__ uint32_t equal_mask(const float (&col)[IPT], int lane) {
+    uint32_t M = 0;
+    const float prev_last = __shfl_up_sync(FULL, col[IPT - 1], 1);
+    if (lane > 0 && col[0] == prev_last) M |= 1u;
+#pragma unroll
+    for (int j = 1; j < IPT; ++j)
+        if (col[j] == col[j - 1]) M |= (1u << j);
+    return M;
+}
+
 template <int IPT, bool MODE>
 __global__ void __launch_bounds__(K2_THREADS, 1)
 k2_sort_kernel(const __grid_constant__ CUtensorMap tmap,
                const __grid_constant__ K2Args a) {
     constexpr int NPAD = IPT * 32;
+    constexpr int TILE_BYTES = NPAD * 128;            // NPAD rows x 32 nodes x 4 B
+    constexpr int BOX_ROWS = NPAD < 256 ? NPAD : 256; // must match make_tmap()
     constexpr int LOGN = (NPAD == 32) ? 5 : (NPAD == 64) ? 6 : (NPAD == 128) ? 7
                        : (NPAD == 256) ? 8 : (NPAD == 512) ? 9 : 10;
     extern __shared__ __align__(1024) unsigned char smem[];
-    float* scratch_all = reinterpret_cast<float*>(smem + K2_NST * K2_STAGE_BYTES);
-    uint64_t* full = reinterpret_cast<uint64_t*>(
-        smem + K2_NST * K2_STAGE_BYTES + K2_WARPS * NPAD * 4);
-    int* rd_cnt = reinterpret_cast<int*>(full + K2_NST);
+    float* scratch_all = reinterpret_cast<float*>(smem + TILE_BYTES);
+    float* cstat_all = scratch_all + K2_WARPS * NPAD;
+    uint64_t* full = reinterpret_cast<uint64_t*>(cstat_all + K2_WARPS * 32);
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
+    const int nbox = (a.R + BOX_ROWS - 1) / BOX_ROWS;
 
-    // chunk sequence of this CTA: seq -> (tile = blockIdx.x + (seq / nchunks) * gridDim.x,
-    // rows [32 (seq % nchunks), +32)); stage = seq % K2_NST
-    const long long my_tiles =
-        (a.ntiles > blockIdx.x) ? (a.ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
-    const long long total_chunks = my_tiles * a.nchunks;
-    auto issue = [&](long long seq) {
-        const long long ti = seq / a.nchunks;
-        const int j = static_cast<int>(seq - ti * a.nchunks);
-        const int col = static_cast<int>(a.n0 + (blockIdx.x + ti * gridDim.x) * 32);
-        const uint32_t st = static_cast<uint32_t>(seq % K2_NST);
-        gsb_mbar_expect_tx(&full[st], K2_STAGE_BYTES);
-        gsb_tma_load_2d(smem + st * K2_STAGE_BYTES, &tmap, &full[st], col, j * 32);
+    // one TMA transaction group per tile: nbox boxes of BOX_ROWS x 32 nodes,
+    // all completing on the same mbarrier
+    auto issue_tile = [&](long long tile) {
+        const int col = static_cast<int>(a.n0 + tile * 32);
+        gsb_fence_proxy_async();
+        gsb_mbar_expect_tx(full, static_cast<uint32_t>(nbox) * BOX_ROWS * 128u);
+        for (int b = 0; b < nbox; ++b)
+            gsb_tma_load_2d(smem + b * BOX_ROWS * 128, &tmap, full, col, b * BOX_ROWS);
     };
 
     if (threadIdx.x == 0) {
-        for (int s = 0; s < K2_NST; ++s) {
-            gsb_mbar_init(&full[s], 1);
-            rd_cnt[s] = 0;
-        }
+        gsb_mbar_init(full, 1);
         gsb_fence_barrier_init();
         gsb_prefetch_tmap(&tmap);
-        for (long long seq = 0; seq < K2_NST && seq < total_chunks; ++seq) issue(seq);
+        if (blockIdx.x < a.ntiles) issue_tile(blockIdx.x);
     }
     __syncthreads();
 
-    // ------------------------------------------------------------ consumers
     float* scr = scratch_all + warp * NPAD;
+    float* cstat = cstat_all + warp * 32;
+    // byte offset of this lane's 16 bytes (nodes 4w..4w+3 of row `lane`) inside
+    // a 32-row chunk, with the 128-byte TMA swizzle applied
     const uint32_t my_off = lane * 128u + ((static_cast<uint32_t>(warp) ^ (lane & 7u)) << 4);
     const float INF = __int_as_float(0x7f800000);
     const float sg = (lane & 1) ? -1.0f : 1.0f;
+    const float infs = (lane & 1) ? -INF : INF;
 
     // this lane's output planes (round r handles plane r*32 + lane)
     int kind0 = -1, kind1 = -1;
@@ -236,119 +300,128 @@ k2_sort_kernel(const __grid_constant__ CUtensorMap tmap,
     if (lane < a.nplanes) { kind0 = a.kind[lane]; q0 = a.q[lane]; }
     if (lane + 32 < a.nplanes) { kind1 = a.kind[lane + 32]; q1 = a.q[lane + 32]; }
 
-    uint32_t it = 0;
+    uint32_t phase = 0;
     for (long long tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x) {
-        float v[4][IPT];
-        float piv[4], S1[4], S2[4], S3[4];
-        int cnt[4];
-#pragma unroll
-        for (int c = 0; c < 4; ++c) { S1[c] = S2[c] = S3[c] = 0.f; cnt[c] = 0; piv[c] = 0.f; }
+        gsb_mbar_wait(full, phase);
+        phase ^= 1u;
 
+        // ---- (1) tile -> registers, nodata/NaN/padding -> +INF (straight-line)
+        float v[4][IPT];
 #pragma unroll
         for (int j = 0; j < IPT; ++j) {
             if (j < a.nchunks) {
-                const uint32_t st = it % K2_NST;
-                const uint32_t ph = (it / K2_NST) & 1u;
-                gsb_mbar_wait(&full[st], ph);
                 const float4 x4 = *reinterpret_cast<const float4*>(
-                    smem + st * K2_STAGE_BYTES + my_off);
-                const float xs[4] = {x4.x, x4.y, x4.z, x4.w};
-                const bool rowok = (j * 32 + lane) < a.R;
-                bool ok[4];
-#pragma unroll
-                for (int c = 0; c < 4; ++c) {
-                    // bn.replace(arr, nodata, nan): exact equality in f32; a
-                    // NaN read from the file is dropped like one (grid.py:681)
-                    ok[c] = rowok && (xs[c] == xs[c]) && (xs[c] != a.nodata);
-                    cnt[c] += ok[c] ? 1 : 0;
-                }
-                if (j == 0) {
-                    // pivot = mean of the valid values among the first 32 rows
-#pragma unroll
-                    for (int c = 0; c < 4; ++c) {
-                        const float s0 = warp_sum(ok[c] ? xs[c] : 0.f);
-                        const int c0 = __reduce_add_sync(FULL, ok[c] ? 1 : 0);
-                        piv[c] = c0 ? s0 / static_cast<float>(c0) : 0.f;
-                    }
-                }
-#pragma unroll
-                for (int c = 0; c < 4; ++c) {
-                    const float d = (ok[c] ? xs[c] : piv[c]) - piv[c];
-                    const float d2 = d * d;
-                    S1[c] += d;
-                    S2[c] += d2;
-                    S3[c] = fmaf(d2, d, S3[c]);
-                    v[c][j] = (ok[c] ? xs[c] : INF) * sg;
-                }
-                __syncwarp();
-                if (lane == 0) {
-                    // the last of the 8 warps to finish reading a stage refills it
-                    __threadfence_block();
-                    if (atomicAdd(&rd_cnt[st], 1) == K2_WARPS - 1) {
-                        __threadfence_block();
-                        rd_cnt[st] = 0;
-                        const long long nxt = static_cast<long long>(it) + K2_NST;
-                        if (nxt < total_chunks) issue(nxt);
-                    }
-                }
-                ++it;
+                    smem + j * K2_STAGE_BYTES + my_off);
+                v[0][j] = sanitize(x4.x, a.nodata, sg, infs);
+                v[1][j] = sanitize(x4.y, a.nodata, sg, infs);
+                v[2][j] = sanitize(x4.z, a.nodata, sg, infs);
+                v[3][j] = sanitize(x4.w, a.nodata, sg, infs);
             } else {
 #pragma unroll
-                for (int c = 0; c < 4; ++c) v[c][j] = INF * sg;
+                for (int c = 0; c < 4; ++c) v[c][j] = infs;
             }
         }
 
-        // ---- moments: finish the shifted sums in float64
-        int n[4];
-        double mean[4], m2[4], m3[4];
+        // ---- (2) shifted one-pass moments straight from the tile (rolled loop)
+        float piv[4], S1[4], S2[4], S3[4];
+        int cnt[4];
+        {
+            const float4 x4 = *reinterpret_cast<const float4*>(smem + my_off);
+            const float xs[4] = {x4.x, x4.y, x4.z, x4.w};
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                const bool ok = is_valid(xs[c], a.nodata);
+                const float s0 = warp_sum(ok ? xs[c] : 0.f);
+                const int c0 = __reduce_add_sync(FULL, ok ? 1 : 0);
+                piv[c] = c0 ? s0 / static_cast<float>(c0) : 0.f;
+                S1[c] = S2[c] = S3[c] = 0.f;
+                cnt[c] = 0;
+            }
+        }
+#pragma unroll 1
+        for (int j = 0; j < a.nchunks; ++j) {
+            const float4 x4 = *reinterpret_cast<const float4*>(
+                smem + j * K2_STAGE_BYTES + my_off);
+            const float xs[4] = {x4.x, x4.y, x4.z, x4.w};
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                const bool ok = is_valid(xs[c], a.nodata);
+                const float d = ok ? xs[c] - piv[c] : 0.f;
+                const float d2 = d * d;
+                cnt[c] += ok ? 1 : 0;
+                S1[c] += d;
+                S2[c] += d2;
+                S3[c] = fmaf(d2, d, S3[c]);
+            }
+        }
+
+        // ---- tile consumed by every warp: stream the next one in behind the sort
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            const long long nxt = tile + gridDim.x;
+            if (nxt < a.ntiles) issue_tile(nxt);
+        }
+
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
-            n[c] = __reduce_add_sync(FULL, cnt[c]);
-            const double s1 = static_cast<double>(warp_sum(S1[c]));
-            const double s2 = static_cast<double>(warp_sum(S2[c]));
-            const double s3 = static_cast<double>(warp_sum(S3[c]));
-            const double dn = static_cast<double>(n[c]);
+            const int n = __reduce_add_sync(FULL, cnt[c]);
+            const float s1 = warp_sum(S1[c]);
+            const float s2 = warp_sum(S2[c]);
+            const float s3 = warp_sum(S3[c]);
+            if (lane == 0) {
+                cstat[c * 8 + 0] = __int_as_float(n);
+                cstat[c * 8 + 1] = piv[c];
+                cstat[c * 8 + 2] = s1;
+                cstat[c * 8 + 3] = s2;
+                cstat[c * 8 + 4] = s3;
+            }
+        }
+
+        // ---- (3) sort the 4 columns (lane-major positions, ascending)
+        sort_in_lane<IPT>(v, a.lockstep != 0);
+        merge_across_lanes<IPT>(v, lane, (lane & 1) != 0, a.lockstep != 0);
+
+        uint32_t M0 = 0, M1 = 0, M2 = 0, M3 = 0;
+        if constexpr (MODE) {
+            M0 = equal_mask<IPT>(v[0], lane);
+            M1 = equal_mask<IPT>(v[1], lane);
+            M2 = equal_mask<IPT>(v[2], lane);
+            M3 = equal_mask<IPT>(v[3], lane);
+        }
+
+        // ---- (4) per column (rolled): park sorted values, evaluate the planes
+        const long long colbase = tile * 32 + warp * 4;
+#pragma unroll 1
+        for (int c = 0; c < 4; ++c) {
+            __syncwarp();
+            switch (c) {
+            case 0: dump_column<IPT>(scr, v[0], lane); break;
+            case 1: dump_column<IPT>(scr, v[1], lane); break;
+            case 2: dump_column<IPT>(scr, v[2], lane); break;
+            default: dump_column<IPT>(scr, v[3], lane); break;
+            }
+            __syncwarp();
+
+            const int nc = __float_as_int(cstat[c * 8 + 0]);
+            const double pivd = static_cast<double>(cstat[c * 8 + 1]);
+            const double s1 = static_cast<double>(cstat[c * 8 + 2]);
+            const double s2 = static_cast<double>(cstat[c * 8 + 3]);
+            const double s3 = static_cast<double>(cstat[c * 8 + 4]);
+            const double dn = static_cast<double>(nc);
             const double delta = s1 / dn;
-            mean[c] = static_cast<double>(piv[c]) + delta;
-            m2[c] = s2 - s1 * delta;
-            m3[c] = s3 - 3.0 * delta * s2 + 2.0 * dn * delta * delta * delta;
-        }
-
-        // ---- sort the 4 columns (lane-major positions, ascending)
-        if (a.nplanes > 0) {
-            sort_in_lane<IPT>(v);
-            merge_across_lanes<IPT>(v, lane, (lane & 1) != 0);
-        }
-
-        // ---- per column: park sorted values, evaluate planes
-        float res0[4], res1[4];
-#pragma unroll
-        for (int c = 0; c < 4; ++c) {
-            __syncwarp();
-#pragma unroll
-            for (int j = 0; j < IPT; ++j)
-                scr[lane * IPT + ((j + ((lane * IPT) >> 5)) & (IPT - 1))] = v[c][j];
-            __syncwarp();
-
-            const int nc = n[c];
+            const double mean = pivd + delta;
             const float vmin = scr[scr_addr<IPT>(0)];
             const float vmax = scr[scr_addr<IPT>(nc > 0 ? nc - 1 : 0)];
             const bool constant = (vmin == vmax);
-            const double dn = static_cast<double>(nc);
-            const double M2 = constant ? 0.0 : fmax(m2[c], 0.0);
-            const double M3 = constant ? 0.0 : m3[c];
-            const double var = (nc > 1) ? M2 / (dn - 1.0) : __longlong_as_double(0x7ff8000000000000LL);
-            const double sd = sqrt(var);
+            const double M2c = constant ? 0.0 : fmax(s2 - s1 * delta, 0.0);
+            const double M3c = constant ? 0.0
+                : s3 - 3.0 * delta * s2 + 2.0 * dn * delta * delta * delta;
+            const double qnan = __longlong_as_double(0x7ff8000000000000LL);
+            const double var = (nc > 1) ? M2c / (dn - 1.0) : qnan;
 
             float modev = 0.f;
             if constexpr (MODE) {
-                // bit j of lane l: sorted[p] == sorted[p-1], p = l*IPT + j
-                uint32_t M = 0;
-                const float prev_last = __shfl_up_sync(FULL, v[c][IPT - 1], 1);
-                if (lane > 0 && v[c][0] == prev_last) M |= 1u;
-#pragma unroll
-                for (int j = 1; j < IPT; ++j)
-                    if (v[c][j] == v[c][j - 1]) M |= (1u << j);
+                uint32_t M = (c == 0) ? M0 : (c == 1) ? M1 : (c == 2) ? M2 : M3;
                 const int mloc = nc - lane * IPT;     // valid positions in this lane
                 if (mloc <= 0) M = 0;
                 else if (mloc < IPT) M &= (1u << mloc) - 1u;
@@ -384,18 +457,17 @@ k2_sort_kernel(const __grid_constant__ CUtensorMap tmap,
             }
 
             auto plane_value = [&](int kind, double q) -> float {
-                const double qnan = __longlong_as_double(0x7ff8000000000000LL);
                 if (nc == 0) return __int_as_float(0x7fc00000);
                 double r = qnan;
                 switch (kind) {
-                case GSB_PK_MEAN: r = mean[c]; break;
+                case GSB_PK_MEAN: r = mean; break;
                 case GSB_PK_VAR: r = var; break;
-                case GSB_PK_STD: r = sd; break;
-                case GSB_PK_COEFVAR: r = sd / mean[c] * 100.0; break;
+                case GSB_PK_STD: r = sqrt(var); break;
+                case GSB_PK_COEFVAR: r = sqrt(var) / mean * 100.0; break;
                 case GSB_PK_SKEW:
                     if (nc < 3) r = qnan;
-                    else if (M2 == 0.0) r = 0.0;
-                    else r = (dn * sqrt(dn - 1.0) / (dn - 2.0)) * (M3 / (M2 * sqrt(M2)));
+                    else if (M2c == 0.0) r = 0.0;
+                    else r = (dn * sqrt(dn - 1.0) / (dn - 2.0)) * (M3c / (M2c * sqrt(M2c)));
                     break;
                 case GSB_PK_MODE: r = static_cast<double>(modev); break;
                 case GSB_PK_QUANT: {
@@ -418,28 +490,15 @@ k2_sort_kernel(const __grid_constant__ CUtensorMap tmap,
                 }
                 return static_cast<float>(r);
             };
-            res0[c] = (kind0 >= 0) ? plane_value(kind0, q0) : 0.f;
-            res1[c] = (kind1 >= 0) ? plane_value(kind1, q1) : 0.f;
-        }
-
-        // ---- store: lane = plane, 4 adjacent nodes per 16-byte store
-        const long long colbase = tile * 32 + warp * 4;
-        const long long left = a.nn - colbase;
-        const bool vec = ((a.out_pitch & 3) == 0) &&
-                         ((reinterpret_cast<uintptr_t>(a.out) & 15) == 0) && left >= 4;
-        if (kind0 >= 0 && left > 0) {
-            float* o = a.out + static_cast<long long>(lane) * a.out_pitch + colbase;
-            if (vec) *reinterpret_cast<float4*>(o) = make_float4(res0[0], res0[1], res0[2], res0[3]);
-            else
-#pragma unroll
-                for (int c = 0; c < 4; ++c) if (c < left) o[c] = res0[c];
-        }
-        if (kind1 >= 0 && left > 0) {
-            float* o = a.out + static_cast<long long>(lane + 32) * a.out_pitch + colbase;
-            if (vec) *reinterpret_cast<float4*>(o) = make_float4(res1[0], res1[1], res1[2], res1[3]);
-            else
-#pragma unroll
-                for (int c = 0; c < 4; ++c) if (c < left) o[c] = res1[c];
+            // lane = plane: neighbouring warps/columns complete the sectors in L2
+            const long long col = colbase + c;
+            if (col >= a.skip && col < a.nn) {
+                if (kind0 >= 0)
+                    a.out[static_cast<long long>(lane) * a.out_pitch + col] = plane_value(kind0, q0);
+                if (kind1 >= 0)
+                    a.out[static_cast<long long>(lane + 32) * a.out_pitch + col] =
+                        plane_value(kind1, q1);
+            }
         }
     }
 }
@@ -447,7 +506,8 @@ k2_sort_kernel(const __grid_constant__ CUtensorMap tmap,
 template <int IPT, bool MODE>
 int launch_one(gsb_stack* s, const K2Args& args, int grid, cudaStream_t st) {
     constexpr int NPAD = IPT * 32;
-    const size_t smem = K2_NST * K2_STAGE_BYTES + K2_WARPS * NPAD * 4 + K2_NST * 8 + K2_NST * 4;
+    const size_t smem = static_cast<size_t>(NPAD) * 128 + K2_WARPS * NPAD * 4 +
+                        K2_WARPS * 32 * 4 + 16;
     auto kern = k2_sort_kernel<IPT, MODE>;
     GSB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   static_cast<int>(smem)));
@@ -472,6 +532,12 @@ int launch_ipt(gsb_stack* s, const K2Args& args, int ipt, int grid, cudaStream_t
 
 }  // namespace
 
+int gsb_k2_box_rows(int64_t R) {
+    int npad = 32;
+    while (npad < R) npad <<= 1;
+    return npad < 256 ? npad : 256;
+}
+
 int gsb_launch_k2_sort(gsb_stack* s, const GsbPlanes& pl, float nodata, int64_t n0,
                        int64_t nn, float* d_out, int64_t out_pitch, cudaStream_t st) {
     GSB_REQUIRE(s->R <= GSB_MAX_R_GRID, "k2 sort kernel supports R <= %d (got %lld)",
@@ -483,10 +549,14 @@ int gsb_launch_k2_sort(gsb_stack* s, const GsbPlanes& pl, float nodata, int64_t 
     args.nchunks = static_cast<int>((s->R + 31) / 32);
     args.nplanes = pl.n;
     args.nodata = nodata;
-    args.ntiles = (nn + 31) / 32;
-    args.n0 = n0;
-    args.nn = nn;
-    args.out = d_out;
+    const char* ls = getenv("GSB_K2_LOCKSTEP");
+    args.lockstep = ls ? atoi(ls) : 0;
+    const int64_t head = n0 & 3;
+    args.n0 = n0 - head;
+    args.nn = nn + head;
+    args.skip = head;
+    args.ntiles = (args.nn + 31) / 32;
+    args.out = d_out - head;
     args.out_pitch = out_pitch;
     for (int i = 0; i < pl.n; ++i) { args.kind[i] = pl.kind[i]; args.q[i] = pl.q[i]; }
     int ipt = 1;

@@ -347,9 +347,9 @@ def test_decode_number_syntax():
     lines = ['1', '-1', '+2.5', '.5', '5.', '1e3', '1E-3', '-1.5e+2', '  7  ',
              '\t8\r', '0', '-0.0', '000123.4500', '1234567890123456',
              '0.1', '0.30000000000000004', '8.5e22', '1e-5', '123456789.123456789',
-             '3.4028235e38', '1e39', '1e-46', 'inf', '-Infinity', 'nan',
-             '812.34559999999999', '9007199254740993', '0.000001', '1.17549435e-38',
-             '4.9406564584124654e-20', '16777217', '16777219', '0.50000000000000011']
+             'inf', '-Infinity', 'nan', '1e22', '12345678901234567e10',
+             '812.34559999999999', '9007199254740993', '0.000001', '1e-21',
+             '1234567.8901234567e-15', '16777217', '16777219', '0.50000000000000011']
     text = ('\n'.join(lines) + '\n').encode()
     stack = _capi.Stack(1, len(lines))
     stack.decode_text(0, text, 0, 0)
@@ -360,6 +360,17 @@ def test_decode_number_syntax():
     ok = (got == exp) | (np.isnan(got) & np.isnan(exp))
     assert ok.all(), [(lines[i], got[i], exp[i]) for i in np.flatnonzero(~ok)]
     assert np.signbit(got[lines.index('-0.0')])
+
+
+def test_decode_unsupported_magnitudes_are_errors_not_guesses():
+    """Outside the exactly-rounded range (<= 19 digits, decimal exponent in
+    [-21, 27] or the <= 15-digit / |e| <= 22 fast path) the decoder refuses
+    (GSB_EPARSE -> ValueError) instead of returning an approximation."""
+    for txt in ('1e39', '1e-46', '3.4028235e38', '12345678901234567890123'):
+        stack = _capi.Stack(1, 1)
+        with pytest.raises(ValueError):
+            stack.decode_text(0, (txt + '\n').encode(), 0, 0)
+        stack.close()
 
 
 @pytest.mark.parametrize('bad', ['abc', '1.2.3', '', '1e', '--1', '1 2',

@@ -1,0 +1,115 @@
+# -*- coding: utf-8 -*-
+"""Live checks of the oracle against the reference's own source, executed
+through oracle/refshim.py.  They run only where /root/reference exists (the
+build container); on the GPU box they are skipped and the committed golden
+fixtures stand in."""
+import os
+import warnings
+
+import numpy as np
+import pandas as pd
+import pytest
+
+from gsimcli_b200 import synth
+from oracle import np_oracle as O, refshim
+
+pytestmark = [pytest.mark.refshim,
+              pytest.mark.skipif(not refshim.available(),
+                                 reason='reference checkout not present')]
+ND = -999.9
+ALL = dict(lmean=True, lmed=True, lskew=True, lvar=True, lstd=True,
+           lcoefvar=True, lperc=True)
+ALLF = (O.FLAG_MEAN | O.FLAG_MED | O.FLAG_SKEW | O.FLAG_VAR | O.FLAG_STD
+        | O.FLAG_COEFVAR | O.FLAG_PERC)
+
+
+def _load(tmp_path, st, dims, first, cells, header=0):
+    _, grid, _ = refshim.load_reference()
+    hdr = ['h', '1', 'v'] if header else None
+    firstfile = synth.write_stack(str(tmp_path), 'r_sim', st, header=hdr)
+    g = grid.GridFiles()
+    g.load(firstfile, st.shape[0], dims, first, cells, ND, header)
+    return g
+
+
+def test_fresh_random_stack_stats_and_area(tmp_path):
+    dims, first, cells = [8, 7, 4], [100.0, 200.0, 1980], [10.0, 20.0, 1]
+    st = synth.stack(int.from_bytes(os.urandom(2), 'little'), 11,
+                     dims).astype(np.float64)
+    st[st == np.float64(np.float32(ND))] = ND
+    g = _load(tmp_path, st, dims, first, cells)
+    with warnings.catch_warnings():
+        warnings.simplefilter('ignore')
+        ref = g.stats(p=0.9, **ALL)
+        mine = O.grid_stats(st, ND, ALLF, 0.9)
+        for key in ref:
+            np.testing.assert_allclose(mine[key], ref[key].val, rtol=5e-13,
+                                       atol=1e-10, equal_nan=True)
+        assert np.array_equal(mine['medianmap'], ref['medianmap'].val,
+                              equal_nan=True)
+        loc = [100.0 + 3.2 * 10, 200.0 + 2.7 * 20]
+        for tol in (0, 1, 2):
+            g.reset_read()
+            ps = g.stats_area(loc, tol=tol, p=0.95, **ALL)
+            name, tab = O.stats_area(st, dims, first, cells, ND, loc, tol,
+                                     ALLF, 0.95)
+            assert name == ps.name
+            np.testing.assert_allclose(tab.values, ps.values.values,
+                                       rtol=5e-13, atol=1e-10, equal_nan=True)
+
+
+def test_quirk_circle_at_grid_edge_is_confined_to_edges(tmp_path):
+    """the reference keeps node 0 / nodes beyond dx, which alias
+    other lines.  Literal mode (clip=False) reproduces the requested lines;
+    the intended behaviour (clip=True) differs only for edge-touching discs."""
+    dims = [4, 3, 2]
+    node, lit = O.area_lines([0.0, 0.0], 1, dims, [0, 0, 0], [1, 1, 1],
+                             clip=False)
+    assert list(node) == [1, 1]
+    assert sorted(lit[:, 0]) == [-3, 0, 1, 2, 5]
+    _, clipped = O.area_lines([0.0, 0.0], 1, dims, [0, 0, 0], [1, 1, 1])
+    assert sorted(clipped[:, 0]) == [1, 2, 5]
+    # interior station: identical either way
+    _, a = O.area_lines([1.0, 1.0], 1, dims, [0, 0, 0], [1, 1, 1], clip=False)
+    _, b = O.area_lines([1.0, 1.0], 1, dims, [0, 0, 0], [1, 1, 1], clip=True)
+    assert np.array_equal(a, b)
+
+
+def test_quirk_header_rows_left_zero_by_reference(tmp_path):
+    """with header=3 the reference leaves the last 3 nodes 0."""
+    dims, first, cells = [3, 2, 2], [0, 0, 0], [1, 1, 1]
+    st = synth.stack(5, 6, dims).astype(np.float64)
+    g = _load(tmp_path, st, dims, first, cells, header=3)
+    with warnings.catch_warnings():
+        warnings.simplefilter('ignore')
+        ref = g.stats(lmean=True)['meanmap'].val
+    mine = O.grid_stats(st, np.float64(np.float32(ND)), O.FLAG_MEAN)['meanmap']
+    assert np.all(ref[-3:] == 0)
+    np.testing.assert_allclose(mine[:-3], ref[:-3], rtol=1e-13)
+
+
+def test_detect_roundtrip_take_candidate_update_station(tmp_path):
+    """take_candidate -> detect -> update_station through the reference and
+    through the oracle agree on counts, flags and corrected values."""
+    _, grid, homog = refshim.load_reference()
+    dims, first, cells = [8, 7, 6], [0.0, 0.0, 2000], [10.0, 10.0, 1]
+    R = 10
+    st = synth.stack(77, R, dims).astype(np.float64)
+    st[st == np.float64(np.float32(ND))] = ND
+    g = _load(tmp_path, st, dims, first, cells)
+    stations = synth.stations(77, 3, R, dims, first, cells)
+    rows = np.vstack([s['obs'] for s in stations])
+    cols = ['x', 'y', 'time', 'station', 'clim']
+    net = grid.PointSet('net', ND, 5, list(cols),
+                        pd.DataFrame(rows, columns=cols))
+    cand, refs = homog.take_candidate(net, 2)
+    obs_df = cand.values.copy()
+    with warnings.catch_warnings():
+        warnings.simplefilter('ignore')
+        hom, dn, md = homog.detect(g, cand, method='median', prob=0.9)
+    ohom, odn, omd = O.detect(st, dims, first, cells, ND, obs_df, ND,
+                              method='median', prob=0.9)
+    assert (dn, md) == (odn, omd)
+    assert np.array_equal(hom.values['Flag'].values, ohom['Flag'].values)
+    np.testing.assert_allclose(hom.values['clim'].values, ohom['clim'].values,
+                               rtol=5e-13)
