@@ -144,10 +144,13 @@ __device__ __forceinline__ void scale_all(float (&v)[4][IPT], float f) {
 template <int IPT>
 __device__ __forceinline__ void merge_across_lanes(float (&v)[4][IPT], int lane,
                                                    bool neg, bool ls_on) {
-#pragma unroll
+    // the phase and stage loops stay ROLLED: one copy of the cross-lane stage
+    // body (IPT*4 x {FMUL, SHFL, FMNMX}) and one of the in-lane half-cleaner
+    // block, re-executed from the instruction cache 15 and 5 times per tile
+#pragma unroll 1
     for (int L = 2; L <= 32; L <<= 1) {
         const bool desc = (L < 32) && ((lane & L) != 0);
-#pragma unroll
+#pragma unroll 1
         for (int ls = L >> 1; ls >= 1; ls >>= 1) {
             // the lane that keeps the larger value works on negated data
             const bool want = ((lane & ls) != 0) != desc;
