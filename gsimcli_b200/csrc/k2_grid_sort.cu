@@ -302,6 +302,12 @@ k2_sort_kernel(const __grid_constant__ CUtensorMap tmap,
     double q0 = 0.0, q1 = 0.0;
     if (lane < a.nplanes) { kind0 = a.kind[lane]; q0 = a.q[lane]; }
     if (lane + 32 < a.nplanes) { kind1 = a.kind[lane + 32]; q1 = a.q[lane + 32]; }
+    // where the parked moment results of a column live: cstat[c*8 + slot]
+    auto slot_of = [](int kind) {
+        return kind == GSB_PK_MEAN ? 1 : kind == GSB_PK_VAR ? 2 : kind == GSB_PK_STD ? 3
+             : kind == GSB_PK_COEFVAR ? 4 : kind == GSB_PK_SKEW ? 5 : 1;
+    };
+    const int slot0 = slot_of(kind0), slot1 = slot_of(kind1);
 
     uint32_t phase = 0;
     for (long long tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x) {
@@ -333,10 +339,23 @@ k2_sort_kernel(const __grid_constant__ CUtensorMap tmap,
             const float xs[4] = {x4.x, x4.y, x4.z, x4.w};
 #pragma unroll
             for (int c = 0; c < 4; ++c) {
+                // pivot: the valid value among the first 32 realizations that is
+                // closest to their mean.  Close to the column mean (no
+                // cancellation in the shifted sums) and an actual element, so
+                // a constant column gives d == 0 and m2 == m3 == 0 exactly.
                 const bool ok = is_valid(xs[c], a.nodata);
                 const float s0 = warp_sum(ok ? xs[c] : 0.f);
                 const int c0 = __reduce_add_sync(FULL, ok ? 1 : 0);
-                piv[c] = c0 ? s0 / static_cast<float>(c0) : 0.f;
+                const float m0 = c0 ? s0 / static_cast<float>(c0) : 0.f;
+                float dist = ok ? fabsf(xs[c] - m0) : INF;
+                float cand = ok ? xs[c] : 0.f;
+#pragma unroll
+                for (int o = 16; o >= 1; o >>= 1) {
+                    const float od = __shfl_xor_sync(FULL, dist, o);
+                    const float oc = __shfl_xor_sync(FULL, cand, o);
+                    if (od < dist || (od == dist && oc < cand)) { dist = od; cand = oc; }
+                }
+                piv[c] = c0 ? cand : 0.f;
                 S1[c] = S2[c] = S3[c] = 0.f;
                 cnt[c] = 0;
             }
@@ -365,18 +384,40 @@ k2_sort_kernel(const __grid_constant__ CUtensorMap tmap,
             if (nxt < a.ntiles) issue_tile(nxt);
         }
 
+        // ---- moment finals, once per tile: lane c finishes column c in float64
+        // and parks the five float32 results the plane lanes will pick up
+        {
+            int n_l = 0;
+            float p_l = 0.f, s1_l = 0.f, s2_l = 0.f, s3_l = 0.f;
 #pragma unroll
-        for (int c = 0; c < 4; ++c) {
-            const int n = __reduce_add_sync(FULL, cnt[c]);
-            const float s1 = warp_sum(S1[c]);
-            const float s2 = warp_sum(S2[c]);
-            const float s3 = warp_sum(S3[c]);
-            if (lane == 0) {
-                cstat[c * 8 + 0] = __int_as_float(n);
-                cstat[c * 8 + 1] = piv[c];
-                cstat[c * 8 + 2] = s1;
-                cstat[c * 8 + 3] = s2;
-                cstat[c * 8 + 4] = s3;
+            for (int c = 0; c < 4; ++c) {
+                const int n = __reduce_add_sync(FULL, cnt[c]);
+                const float s1 = warp_sum(S1[c]);
+                const float s2 = warp_sum(S2[c]);
+                const float s3 = warp_sum(S3[c]);
+                if (lane == c) { n_l = n; p_l = piv[c]; s1_l = s1; s2_l = s2; s3_l = s3; }
+            }
+            if (lane < 4) {
+                const float fnan = __int_as_float(0x7fc00000);
+                const double dn = static_cast<double>(n_l);
+                const double d1 = static_cast<double>(s1_l), d2 = static_cast<double>(s2_l);
+                const double delta = d1 / dn;
+                const double mean = static_cast<double>(p_l) + delta;
+                const bool constant = (s2_l == 0.f);
+                const double m2 = constant ? 0.0 : fmax(d2 - d1 * delta, 0.0);
+                const double m3 = constant ? 0.0
+                    : static_cast<double>(s3_l) - 3.0 * delta * d2 + 2.0 * dn * delta * delta * delta;
+                const double var = m2 / (dn - 1.0);
+                const double sd = sqrt(var);
+                float* o = cstat + lane * 8;
+                o[0] = __int_as_float(n_l);
+                o[1] = n_l > 0 ? static_cast<float>(mean) : fnan;
+                o[2] = n_l > 1 ? static_cast<float>(var) : fnan;
+                o[3] = n_l > 1 ? static_cast<float>(sd) : fnan;
+                o[4] = n_l > 1 ? static_cast<float>(sd / mean * 100.0) : fnan;
+                o[5] = n_l < 3 ? fnan
+                     : (m2 == 0.0) ? 0.f
+                     : static_cast<float>((dn * sqrt(dn - 1.0) / (dn - 2.0)) * (m3 / (m2 * sqrt(m2))));
             }
         }
 
@@ -406,21 +447,12 @@ k2_sort_kernel(const __grid_constant__ CUtensorMap tmap,
             __syncwarp();
 
             const int nc = __float_as_int(cstat[c * 8 + 0]);
-            const double pivd = static_cast<double>(cstat[c * 8 + 1]);
-            const double s1 = static_cast<double>(cstat[c * 8 + 2]);
-            const double s2 = static_cast<double>(cstat[c * 8 + 3]);
-            const double s3 = static_cast<double>(cstat[c * 8 + 4]);
             const double dn = static_cast<double>(nc);
-            const double delta = s1 / dn;
-            const double mean = pivd + delta;
             const float vmin = scr[scr_addr<IPT>(0)];
             const float vmax = scr[scr_addr<IPT>(nc > 0 ? nc - 1 : 0)];
+            // a column whose first 32 realizations are all missing has pivot 0:
+            // enforce the exact zeros of a constant column from the sorted ends
             const bool constant = (vmin == vmax);
-            const double M2c = constant ? 0.0 : fmax(s2 - s1 * delta, 0.0);
-            const double M3c = constant ? 0.0
-                : s3 - 3.0 * delta * s2 + 2.0 * dn * delta * delta * delta;
-            const double qnan = __longlong_as_double(0x7ff8000000000000LL);
-            const double var = (nc > 1) ? M2c / (dn - 1.0) : qnan;
 
             float modev = 0.f;
             if constexpr (MODE) {
@@ -459,48 +491,42 @@ k2_sort_kernel(const __grid_constant__ CUtensorMap tmap,
                 modev = scr[scr_addr<IPT>(pe)];
             }
 
-            auto plane_value = [&](int kind, double q) -> float {
-                if (nc == 0) return __int_as_float(0x7fc00000);
-                double r = qnan;
-                switch (kind) {
-                case GSB_PK_MEAN: r = mean; break;
-                case GSB_PK_VAR: r = var; break;
-                case GSB_PK_STD: r = sqrt(var); break;
-                case GSB_PK_COEFVAR: r = sqrt(var) / mean * 100.0; break;
-                case GSB_PK_SKEW:
-                    if (nc < 3) r = qnan;
-                    else if (M2c == 0.0) r = 0.0;
-                    else r = (dn * sqrt(dn - 1.0) / (dn - 2.0)) * (M3c / (M2c * sqrt(M2c)));
-                    break;
-                case GSB_PK_MODE: r = static_cast<double>(modev); break;
-                case GSB_PK_QUANT: {
+            auto plane_value = [&](int kind, int slot, double q) -> float {
+                const float fnan = __int_as_float(0x7fc00000);
+                if (nc == 0) return fnan;
+                if (kind == GSB_PK_QUANT) {
                     // np.quantile(method='linear'): h = (n-1) q, NumPy _lerp
                     const double h = __dmul_rn(dn - 1.0, q);
-                    if (h >= dn - 1.0) r = static_cast<double>(vmax);
-                    else if (h < 0.0) r = static_cast<double>(vmin);
-                    else {
-                        const double fl = floor(h);
-                        const int lo = static_cast<int>(fl);
-                        const double t = h - fl;
-                        const double x0 = static_cast<double>(scr[scr_addr<IPT>(lo)]);
-                        const double x1 = static_cast<double>(scr[scr_addr<IPT>(lo + 1)]);
-                        const double d = x1 - x0;
-                        r = (t >= 0.5) ? __dsub_rn(x1, __dmul_rn(d, 1.0 - t))
-                                       : __dadd_rn(x0, __dmul_rn(d, t));
-                    }
-                } break;
-                default: break;
+                    if (h >= dn - 1.0) return vmax;
+                    if (h < 0.0) return vmin;
+                    const double fl = floor(h);
+                    const int lo = static_cast<int>(fl);
+                    const double t = h - fl;
+                    const double x0 = static_cast<double>(scr[scr_addr<IPT>(lo)]);
+                    const double x1 = static_cast<double>(scr[scr_addr<IPT>(lo + 1)]);
+                    const double d = x1 - x0;
+                    const double r = (t >= 0.5) ? __dsub_rn(x1, __dmul_rn(d, 1.0 - t))
+                                                : __dadd_rn(x0, __dmul_rn(d, t));
+                    return static_cast<float>(r);
                 }
-                return static_cast<float>(r);
+                if (kind == GSB_PK_MODE) return modev;
+                float r = cstat[c * 8 + slot];
+                if (constant && slot >= 2) {
+                    if (slot == 4) r = (nc > 1) ? 0.f / cstat[c * 8 + 1] * 100.f : fnan;
+                    else if (slot == 5) r = (nc >= 3) ? 0.f : fnan;
+                    else r = (nc > 1) ? 0.f : fnan;
+                }
+                return r;
             };
             // lane = plane: neighbouring warps/columns complete the sectors in L2
             const long long col = colbase + c;
             if (col >= a.skip && col < a.nn) {
                 if (kind0 >= 0)
-                    a.out[static_cast<long long>(lane) * a.out_pitch + col] = plane_value(kind0, q0);
+                    a.out[static_cast<long long>(lane) * a.out_pitch + col] =
+                        plane_value(kind0, slot0, q0);
                 if (kind1 >= 0)
                     a.out[static_cast<long long>(lane + 32) * a.out_pitch + col] =
-                        plane_value(kind1, q1);
+                        plane_value(kind1, slot1, q1);
             }
         }
     }
