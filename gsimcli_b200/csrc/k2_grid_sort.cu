@@ -30,8 +30,6 @@
 
 namespace {
 
-constexpr int K2_WARPS = 8;
-constexpr int K2_THREADS = K2_WARPS * 32;
 constexpr int K2_STAGE_BYTES = 4096;   // 32 rows x 32 nodes x 4 B
 constexpr int K2_NST = 32;             // ring depth: one full R=1024 tile
 constexpr unsigned FULL = 0xffffffffu;
@@ -41,6 +39,7 @@ struct K2Args {
     int nchunks;
     int nplanes;
     int lockstep;      // experiment knob: block barriers inside the sort (GSB_K2_LOCKSTEP)
+    int skew;          // warps 4..7 run the in-lane sort before the tile barrier (GSB_K2_SKEW)
     float nodata;
     long long ntiles;
     long long n0;      // first column of tile 0 (multiple of 4: TMA needs 16-byte aligned boxes)
@@ -83,10 +82,10 @@ struct Oem {
     static constexpr OemNet<IPT> net = make_oem<IPT>();
 };
 
-template <int I, int J, int IPT>
-__device__ __forceinline__ void ce4(float (&v)[4][IPT]) {
+template <int I, int J, int CPW, int IPT>
+__device__ __forceinline__ void ce4(float (&v)[CPW][IPT]) {
 #pragma unroll
-    for (int c = 0; c < 4; ++c) {
+    for (int c = 0; c < CPW; ++c) {
         const float x = v[c][I], y = v[c][J];
         v[c][I] = fminf(x, y);
         v[c][J] = fmaxf(x, y);
@@ -106,16 +105,16 @@ __device__ __forceinline__ void lockstep_every(bool on) {
     if constexpr ((I % 48) == 47) { if (on) lockstep(); }
 }
 
-template <int IPT, int... Is>
-__device__ __forceinline__ void oem_apply(float (&v)[4][IPT], bool ls,
+template <int CPW, int IPT, int... Is>
+__device__ __forceinline__ void oem_apply(float (&v)[CPW][IPT], bool ls,
                                           std::integer_sequence<int, Is...>) {
-    ((ce4<Oem<IPT>::net.a[Is], Oem<IPT>::net.b[Is], IPT>(v), lockstep_every<Is>(ls)), ...);
+    ((ce4<Oem<IPT>::net.a[Is], Oem<IPT>::net.b[Is], CPW, IPT>(v), lockstep_every<Is>(ls)), ...);
 }
 
-template <int IPT>
-__device__ __forceinline__ void sort_in_lane(float (&v)[4][IPT], bool ls) {
+template <int CPW, int IPT>
+__device__ __forceinline__ void sort_in_lane(float (&v)[CPW][IPT], bool ls) {
     if constexpr (IPT > 1)
-        oem_apply<IPT>(v, ls, std::make_integer_sequence<int, Oem<IPT>::net.n>{});
+        oem_apply<CPW, IPT>(v, ls, std::make_integer_sequence<int, Oem<IPT>::net.n>{});
 }
 
 // v *= f with f = +-1.  Inline PTX keeps it an FMUL (fma pipe, idle here):
@@ -127,10 +126,10 @@ __device__ __forceinline__ float mul_sign(float x, float f) {
     return r;
 }
 
-template <int IPT>
-__device__ __forceinline__ void scale_all(float (&v)[4][IPT], float f) {
+template <int CPW, int IPT>
+__device__ __forceinline__ void scale_all(float (&v)[CPW][IPT], float f) {
 #pragma unroll
-    for (int c = 0; c < 4; ++c)
+    for (int c = 0; c < CPW; ++c)
 #pragma unroll
         for (int j = 0; j < IPT; ++j) v[c][j] = mul_sign(v[c][j], f);
 }
@@ -141,8 +140,8 @@ __device__ __forceinline__ void scale_all(float (&v)[4][IPT], float f) {
 // On entry every lane is sorted ascending in ITS stored values, and lanes with
 // (lane & 1) hold negated values (i.e. are descending in x).  `neg` tracks the
 // lane's sign state.  On exit all lanes hold plain x, globally ascending.
-template <int IPT>
-__device__ __forceinline__ void merge_across_lanes(float (&v)[4][IPT], int lane,
+template <int CPW, int IPT>
+__device__ __forceinline__ void merge_across_lanes(float (&v)[CPW][IPT], int lane,
                                                    bool neg, bool ls_on) {
     // the phase and stage loops stay ROLLED: one copy of the cross-lane stage
     // body (IPT*4 x {FMUL, SHFL, FMNMX}) and one of the in-lane half-cleaner
@@ -154,10 +153,10 @@ __device__ __forceinline__ void merge_across_lanes(float (&v)[4][IPT], int lane,
         for (int ls = L >> 1; ls >= 1; ls >>= 1) {
             // the lane that keeps the larger value works on negated data
             const bool want = ((lane & ls) != 0) != desc;
-            scale_all<IPT>(v, (want != neg) ? -1.0f : 1.0f);
+            scale_all<CPW, IPT>(v, (want != neg) ? -1.0f : 1.0f);
             neg = want;
 #pragma unroll
-            for (int c = 0; c < 4; ++c)
+            for (int c = 0; c < CPW; ++c)
 #pragma unroll
                 for (int j = 0; j < IPT; ++j) {
                     const float o = __shfl_xor_sync(FULL, v[c][j], ls);
@@ -166,7 +165,7 @@ __device__ __forceinline__ void merge_across_lanes(float (&v)[4][IPT], int lane,
             if constexpr (IPT >= 8) { if (ls_on) lockstep(); }
         }
         if constexpr (IPT > 1) {
-            scale_all<IPT>(v, (desc != neg) ? -1.0f : 1.0f);
+            scale_all<CPW, IPT>(v, (desc != neg) ? -1.0f : 1.0f);
             neg = desc;
 #pragma unroll
             for (int s = IPT >> 1; s >= 1; s >>= 1)
@@ -174,7 +173,7 @@ __device__ __forceinline__ void merge_across_lanes(float (&v)[4][IPT], int lane,
                 for (int j = 0; j < IPT; ++j)
                     if ((j & s) == 0) {
 #pragma unroll
-                        for (int c = 0; c < 4; ++c) {
+                        for (int c = 0; c < CPW; ++c) {
                             const float x = v[c][j], y = v[c][j | s];
                             v[c][j] = fminf(x, y);
                             v[c][j | s] = fmaxf(x, y);
@@ -182,7 +181,7 @@ __device__ __forceinline__ void merge_across_lanes(float (&v)[4][IPT], int lane,
                     }
             if constexpr (IPT >= 8) { if (ls_on) lockstep(); }
         } else {
-            scale_all<IPT>(v, (desc != neg) ? -1.0f : 1.0f);
+            scale_all<CPW, IPT>(v, (desc != neg) ? -1.0f : 1.0f);
             neg = desc;
         }
     }
@@ -252,10 +251,13 @@ __device__ __forceinline__ uint32_t equal_mask(const float (&col)[IPT], int lane
     return M;
 }
 
-template <int IPT, bool MODE>
-__global__ void __launch_bounds__(K2_THREADS, 1)
+// CPW = nodes (columns) per warp: 4 -> 8 warps x 255 registers, 2 -> 16 warps x
+// 128 registers (more warps per scheduler to cover SHFL / FMNMX latencies).
+template <int IPT, bool MODE, int CPW>
+__global__ void __launch_bounds__(32 / CPW * 32, 1)
 k2_sort_kernel(const __grid_constant__ CUtensorMap tmap,
                const __grid_constant__ K2Args a) {
+    constexpr int K2_WARPS = 32 / CPW;
     constexpr int NPAD = IPT * 32;
     constexpr int TILE_BYTES = NPAD * 128;            // NPAD rows x 32 nodes x 4 B
     constexpr int BOX_ROWS = NPAD < 256 ? NPAD : 256; // must match make_tmap()
@@ -292,7 +294,19 @@ k2_sort_kernel(const __grid_constant__ CUtensorMap tmap,
     float* cstat = cstat_all + warp * 32;
     // byte offset of this lane's 16 bytes (nodes 4w..4w+3 of row `lane`) inside
     // a 32-row chunk, with the 128-byte TMA swizzle applied
-    const uint32_t my_off = lane * 128u + ((static_cast<uint32_t>(warp) ^ (lane & 7u)) << 4);
+    const uint32_t my_off = (CPW == 4)
+        ? lane * 128u + ((static_cast<uint32_t>(warp) ^ (lane & 7u)) << 4)
+        : lane * 128u + (((static_cast<uint32_t>(warp) >> 1) ^ (lane & 7u)) << 4) + (warp & 1u) * 8u;
+    auto load_row = [&](int j, float (&xs)[CPW]) {
+        const unsigned char* ptr = smem + j * K2_STAGE_BYTES + my_off;
+        if constexpr (CPW == 4) {
+            const float4 t = *reinterpret_cast<const float4*>(ptr);
+            xs[0] = t.x; xs[1] = t.y; xs[2] = t.z; xs[3] = t.w;
+        } else {
+            const float2 t = *reinterpret_cast<const float2*>(ptr);
+            xs[0] = t.x; xs[1] = t.y;
+        }
+    };
     const float INF = __int_as_float(0x7f800000);
     const float sg = (lane & 1) ? -1.0f : 1.0f;
     const float infs = (lane & 1) ? -INF : INF;
@@ -315,30 +329,28 @@ k2_sort_kernel(const __grid_constant__ CUtensorMap tmap,
         phase ^= 1u;
 
         // ---- (1) tile -> registers, nodata/NaN/padding -> +INF (straight-line)
-        float v[4][IPT];
+        float v[CPW][IPT];
 #pragma unroll
         for (int j = 0; j < IPT; ++j) {
             if (j < a.nchunks) {
-                const float4 x4 = *reinterpret_cast<const float4*>(
-                    smem + j * K2_STAGE_BYTES + my_off);
-                v[0][j] = sanitize(x4.x, a.nodata, sg, infs);
-                v[1][j] = sanitize(x4.y, a.nodata, sg, infs);
-                v[2][j] = sanitize(x4.z, a.nodata, sg, infs);
-                v[3][j] = sanitize(x4.w, a.nodata, sg, infs);
+                float xs[CPW];
+                load_row(j, xs);
+#pragma unroll
+                for (int c = 0; c < CPW; ++c) v[c][j] = sanitize(xs[c], a.nodata, sg, infs);
             } else {
 #pragma unroll
-                for (int c = 0; c < 4; ++c) v[c][j] = infs;
+                for (int c = 0; c < CPW; ++c) v[c][j] = infs;
             }
         }
 
         // ---- (2) shifted one-pass moments straight from the tile (rolled loop)
-        float piv[4], S1[4], S2[4], S3[4];
-        int cnt[4];
+        float piv[CPW], S1[CPW], S2[CPW], S3[CPW];
+        int cnt[CPW];
         {
-            const float4 x4 = *reinterpret_cast<const float4*>(smem + my_off);
-            const float xs[4] = {x4.x, x4.y, x4.z, x4.w};
+            float xs[CPW];
+            load_row(0, xs);
 #pragma unroll
-            for (int c = 0; c < 4; ++c) {
+            for (int c = 0; c < CPW; ++c) {
                 // pivot: the valid value among the first 32 realizations that is
                 // closest to their mean.  Close to the column mean (no
                 // cancellation in the shifted sums) and an actual element, so
@@ -362,11 +374,10 @@ k2_sort_kernel(const __grid_constant__ CUtensorMap tmap,
         }
 #pragma unroll 1
         for (int j = 0; j < a.nchunks; ++j) {
-            const float4 x4 = *reinterpret_cast<const float4*>(
-                smem + j * K2_STAGE_BYTES + my_off);
-            const float xs[4] = {x4.x, x4.y, x4.z, x4.w};
+            float xs[CPW];
+            load_row(j, xs);
 #pragma unroll
-            for (int c = 0; c < 4; ++c) {
+            for (int c = 0; c < CPW; ++c) {
                 const bool ok = is_valid(xs[c], a.nodata);
                 const float d = ok ? xs[c] - piv[c] : 0.f;
                 const float d2 = d * d;
@@ -377,11 +388,24 @@ k2_sort_kernel(const __grid_constant__ CUtensorMap tmap,
             }
         }
 
-        // ---- tile consumed by every warp: stream the next one in behind the sort
-        __syncthreads();
-        if (threadIdx.x == 0) {
-            const long long nxt = tile + gridDim.x;
-            if (nxt < a.ntiles) issue_tile(nxt);
+        // ---- in-lane sort + release of the tile.  Warps 4..7 sort their lanes
+        // BEFORE the block barrier, warps 0..3 after it, so the two warps that
+        // share a scheduler (w and w+4) run about one merge phase apart: one is
+        // in a SHFL-bound cross-lane stage while the other is in an FMNMX-bound
+        // in-lane stage.  (One copy of the network: the loop is not unrolled.)
+#pragma unroll 1
+        for (int rep = 0; rep < 2; ++rep) {
+            if (((warp & 4) != 0) == (rep == 0) || a.skew == 0) {
+                if (a.skew != 0 || rep == 1) sort_in_lane<CPW, IPT>(v, a.lockstep != 0);
+            }
+            if (rep == 0) {
+                // tile consumed by every warp: stream the next one in behind the sort
+                __syncthreads();
+                if (threadIdx.x == 0) {
+                    const long long nxt = tile + gridDim.x;
+                    if (nxt < a.ntiles) issue_tile(nxt);
+                }
+            }
         }
 
         // ---- moment finals, once per tile: lane c finishes column c in float64
@@ -390,14 +414,14 @@ k2_sort_kernel(const __grid_constant__ CUtensorMap tmap,
             int n_l = 0;
             float p_l = 0.f, s1_l = 0.f, s2_l = 0.f, s3_l = 0.f;
 #pragma unroll
-            for (int c = 0; c < 4; ++c) {
+            for (int c = 0; c < CPW; ++c) {
                 const int n = __reduce_add_sync(FULL, cnt[c]);
                 const float s1 = warp_sum(S1[c]);
                 const float s2 = warp_sum(S2[c]);
                 const float s3 = warp_sum(S3[c]);
                 if (lane == c) { n_l = n; p_l = piv[c]; s1_l = s1; s2_l = s2; s3_l = s3; }
             }
-            if (lane < 4) {
+            if (lane < CPW) {
                 const float fnan = __int_as_float(0x7fc00000);
                 const double dn = static_cast<double>(n_l);
                 const double d1 = static_cast<double>(s1_l), d2 = static_cast<double>(s2_l);
@@ -421,28 +445,34 @@ k2_sort_kernel(const __grid_constant__ CUtensorMap tmap,
             }
         }
 
-        // ---- (3) sort the 4 columns (lane-major positions, ascending)
-        sort_in_lane<IPT>(v, a.lockstep != 0);
-        merge_across_lanes<IPT>(v, lane, (lane & 1) != 0, a.lockstep != 0);
+        // ---- (3) merge the sorted lanes (lane-major positions, ascending)
+        merge_across_lanes<CPW, IPT>(v, lane, (lane & 1) != 0, a.lockstep != 0);
 
         uint32_t M0 = 0, M1 = 0, M2 = 0, M3 = 0;
         if constexpr (MODE) {
             M0 = equal_mask<IPT>(v[0], lane);
             M1 = equal_mask<IPT>(v[1], lane);
-            M2 = equal_mask<IPT>(v[2], lane);
-            M3 = equal_mask<IPT>(v[3], lane);
+            if constexpr (CPW == 4) {
+                M2 = equal_mask<IPT>(v[2], lane);
+                M3 = equal_mask<IPT>(v[3], lane);
+            }
         }
 
         // ---- (4) per column (rolled): park sorted values, evaluate the planes
-        const long long colbase = tile * 32 + warp * 4;
+        const long long colbase = tile * 32 + warp * CPW;
 #pragma unroll 1
-        for (int c = 0; c < 4; ++c) {
+        for (int c = 0; c < CPW; ++c) {
             __syncwarp();
-            switch (c) {
-            case 0: dump_column<IPT>(scr, v[0], lane); break;
-            case 1: dump_column<IPT>(scr, v[1], lane); break;
-            case 2: dump_column<IPT>(scr, v[2], lane); break;
-            default: dump_column<IPT>(scr, v[3], lane); break;
+            if constexpr (CPW == 4) {
+                switch (c) {
+                case 0: dump_column<IPT>(scr, v[0], lane); break;
+                case 1: dump_column<IPT>(scr, v[1], lane); break;
+                case 2: dump_column<IPT>(scr, v[2], lane); break;
+                default: dump_column<IPT>(scr, v[CPW - 1], lane); break;
+                }
+            } else {
+                if (c == 0) dump_column<IPT>(scr, v[0], lane);
+                else dump_column<IPT>(scr, v[CPW - 1], lane);
             }
             __syncwarp();
 
@@ -532,28 +562,28 @@ k2_sort_kernel(const __grid_constant__ CUtensorMap tmap,
     }
 }
 
-template <int IPT, bool MODE>
+template <int IPT, bool MODE, int CPW>
 int launch_one(gsb_stack* s, const K2Args& args, int grid, cudaStream_t st) {
     constexpr int NPAD = IPT * 32;
-    const size_t smem = static_cast<size_t>(NPAD) * 128 + K2_WARPS * NPAD * 4 +
-                        K2_WARPS * 32 * 4 + 16;
-    auto kern = k2_sort_kernel<IPT, MODE>;
+    constexpr int WARPS = 32 / CPW;
+    const size_t smem = static_cast<size_t>(NPAD) * 128 + WARPS * NPAD * 4 + WARPS * 32 * 4 + 16;
+    auto kern = k2_sort_kernel<IPT, MODE, CPW>;
     GSB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   static_cast<int>(smem)));
-    kern<<<grid, K2_THREADS, smem, st>>>(s->tmap_k2, args);
+    kern<<<grid, WARPS * 32, smem, st>>>(s->tmap_k2, args);
     GSB_CUDA(cudaGetLastError());
     return GSB_OK;
 }
 
-template <bool MODE>
+template <bool MODE, int CPW>
 int launch_ipt(gsb_stack* s, const K2Args& args, int ipt, int grid, cudaStream_t st) {
     switch (ipt) {
-    case 1: return launch_one<1, MODE>(s, args, grid, st);
-    case 2: return launch_one<2, MODE>(s, args, grid, st);
-    case 4: return launch_one<4, MODE>(s, args, grid, st);
-    case 8: return launch_one<8, MODE>(s, args, grid, st);
-    case 16: return launch_one<16, MODE>(s, args, grid, st);
-    case 32: return launch_one<32, MODE>(s, args, grid, st);
+    case 1: return launch_one<1, MODE, CPW>(s, args, grid, st);
+    case 2: return launch_one<2, MODE, CPW>(s, args, grid, st);
+    case 4: return launch_one<4, MODE, CPW>(s, args, grid, st);
+    case 8: return launch_one<8, MODE, CPW>(s, args, grid, st);
+    case 16: return launch_one<16, MODE, CPW>(s, args, grid, st);
+    case 32: return launch_one<32, MODE, CPW>(s, args, grid, st);
     }
     gsb_set_error("k2: unsupported items-per-lane %d", ipt);
     return GSB_EINVAL;
@@ -580,6 +610,8 @@ int gsb_launch_k2_sort(gsb_stack* s, const GsbPlanes& pl, float nodata, int64_t 
     args.nodata = nodata;
     const char* ls = getenv("GSB_K2_LOCKSTEP");
     args.lockstep = ls ? atoi(ls) : 0;
+    const char* sk = getenv("GSB_K2_SKEW");
+    args.skew = sk ? atoi(sk) : 1;
     const int64_t head = n0 & 3;
     args.n0 = n0 - head;
     args.nn = nn + head;
@@ -592,6 +624,11 @@ int gsb_launch_k2_sort(gsb_stack* s, const GsbPlanes& pl, float nodata, int64_t 
     while (ipt * 32 < s->R) ipt <<= 1;
     const int grid = static_cast<int>(args.ntiles < s->sm_count ? args.ntiles : s->sm_count);
     if (grid <= 0) return GSB_OK;
-    return pl.need_mode ? launch_ipt<true>(s, args, ipt, grid, st)
-                        : launch_ipt<false>(s, args, ipt, grid, st);
+    const char* cp = getenv("GSB_K2_CPW");
+    const int cpw = cp ? atoi(cp) : 2;
+    if (cpw == 2)
+        return pl.need_mode ? launch_ipt<true, 2>(s, args, ipt, grid, st)
+                            : launch_ipt<false, 2>(s, args, ipt, grid, st);
+    return pl.need_mode ? launch_ipt<true, 4>(s, args, ipt, grid, st)
+                        : launch_ipt<false, 4>(s, args, ipt, grid, st);
 }
