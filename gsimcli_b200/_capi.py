@@ -48,6 +48,7 @@ SIGNATURES = {
     'gsb_stack_destroy': (C.c_int, [c_vp]),
     'gsb_stack_info': (C.c_int, [c_vp, p_i64, p_i64, p_i64,
                                  C.POINTER(C.c_int)]),
+    'gsb_stack_set_option': (C.c_int, [c_vp, C.c_char_p, c_i64]),
     'gsb_stack_device_ptr': (C.c_int, [c_vp, C.POINTER(c_vp)]),
     'gsb_stack_upload_f32': (C.c_int, [c_vp, c_i64, c_i64, c_i64, c_i64, c_vp,
                                        c_i64, c_vp]),
@@ -170,6 +171,9 @@ class Stack(object):
         self.handle = None
 
     __del__ = close
+
+    def set_option(self, key, value):
+        check(lib().gsb_stack_set_option(self.handle, key.encode(), int(value)))
 
     def device_ptr(self):
         p = c_vp()

@@ -200,6 +200,17 @@ int gsb_stack_info(const gsb_stack* s, int64_t* R, int64_t* N, int64_t* pitch, i
     return GSB_OK;
 }
 
+int gsb_stack_set_option(gsb_stack* s, const char* key, int64_t value) {
+    GSB_REQUIRE(s && key, "NULL argument");
+    if (strcmp(key, "k2_sm_reserve") == 0) {
+        GSB_REQUIRE(value >= 0 && value < s->sm_count, "k2_sm_reserve out of range");
+        s->k2_sm_reserve = (int)value;
+        return GSB_OK;
+    }
+    gsb_set_error("unknown option '%s'", key);
+    return GSB_EINVAL;
+}
+
 int gsb_stack_device_ptr(const gsb_stack* s, void** dptr) {
     GSB_REQUIRE(s && dptr, "NULL argument");
     *dptr = s->data;

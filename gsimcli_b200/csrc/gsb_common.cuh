@@ -53,6 +53,7 @@ struct gsb_stack {
     CUtensorMap tmap_k2;   // 2-D map (node, realization): box 32 nodes x
                            // gsb_k2_box_rows(R) rows, 128B swizzle, OOB -> NaN
     int tmap_ok;
+    int k2_sm_reserve;     // SMs the K2 grid leaves free (gsb_stack_set_option)
 };
 
 int gsb_scratch(gsb_stack* s, size_t bytes, void** out);

@@ -622,7 +622,8 @@ int gsb_launch_k2_sort(gsb_stack* s, const GsbPlanes& pl, float nodata, int64_t 
     for (int i = 0; i < pl.n; ++i) { args.kind[i] = pl.kind[i]; args.q[i] = pl.q[i]; }
     int ipt = 1;
     while (ipt * 32 < s->R) ipt <<= 1;
-    const int grid = static_cast<int>(args.ntiles < s->sm_count ? args.ntiles : s->sm_count);
+    const int ctas = s->sm_count - s->k2_sm_reserve;
+    const int grid = static_cast<int>(args.ntiles < ctas ? args.ntiles : ctas);
     if (grid <= 0) return GSB_OK;
     const char* cp = getenv("GSB_K2_CPW");
     const int cpw = cp ? atoi(cp) : 2;

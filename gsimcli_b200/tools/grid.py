@@ -398,8 +398,11 @@ class GridFiles(object):
         node = coord_to_grid(loc, [self.cellx, self.celly, self.cellz],
                              [self.xi, self.yi, self.zi])[:2]
         nodes = circle(node[0], node[1], tol, dims)
-        lines = np.array([line_zmirror(nd, dims) for nd in nodes],
-                         dtype=np.int64).reshape(len(nodes), self.dz)
+        # line_zmirror for every neighbour at once: 1-based line of (x, y, z)
+        # = x + dx (y - 1) + dx dy (z - 1)   (grid.py:978-979)
+        base = nodes[:, 0].astype(np.int64) + self.dx * (nodes[:, 1] - 1)
+        lines = base[:, None] + self.dx * self.dy * np.arange(self.dz,
+                                                              dtype=np.int64)
         lines = np.sort(lines, axis=0)
         ids = lines.T - 1 - self.node0                       # [dz][K]
         n = self._need_stack().N
@@ -409,9 +412,10 @@ class GridFiles(object):
     def stats_area_many(self, locs, tol=0, lmean=False, lmed=False,
                         lskew=False, lvar=False, lstd=False, lcoefvar=False,
                         lperc=False, p=0.95, save=False, percentiles=None,
-                        lmode=False):
+                        lmode=False, stream=None):
         """Extension: ``stats_area`` for many locations with one kernel
-        launch.  Returns a list of ``PointSet``."""
+        launch.  Returns a list of ``PointSet``.  ``stream`` is an optional
+        ``cudaStream_t`` handle (int) to enqueue on."""
         stack = self._need_stack()
         sel = dict(lmean=lmean, lmed=lmed, lskew=lskew, lvar=lvar, lstd=lstd,
                    lcoefvar=lcoefvar, lperc=lperc, lmode=lmode)
@@ -433,7 +437,8 @@ class GridFiles(object):
         if lmode:
             names += ['mode']
         if len(names) > 3:
-            table = stack.stats_columns(ids, flags, p, percentiles, self.nodata)
+            table = stack.stats_columns(ids, flags, p, percentiles, self.nodata,
+                                        stream)
             if self.sharded:
                 # node-sharded stack: rows are valid for this rank's time
                 # layers only; gather the small tables (NCCL over NVLink)

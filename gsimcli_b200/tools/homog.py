@@ -47,7 +47,8 @@ def _prepare_obs(obs, grids, header):
         path = obs
         obs = gr.PointSet()
         obs.load(path, header=header)
-    obs_xy = list(obs.values.loc[obs.values.first_valid_index(), ['x', 'y']])
+    first = obs.values.index.get_loc(obs.values.first_valid_index())
+    obs_xy = [obs.values['x'].values[first], obs.values['y'].values[first]]
     if 'Flag' in obs.values.columns:
         obs.values = obs.values.drop('Flag', axis=1)
     if 'Flag' in obs.varnames:
@@ -64,14 +65,28 @@ def _finish(obs, local, fixcols, method, skewness, hom_in, flag,
     (homog.py:204-269)."""
     filled, homog, flagcol, det = hom_in
     obs.values['clim'] = filled
-    homogenised = gr.PointSet(obs.name + '_homogenised', obs.nodata, obs.nvars,
-                              list(obs.varnames), obs.values.copy())
-    # placeholders of optional statistics are all-NaN columns (homog.py:212)
-    homogenised.values = homogenised.values.dropna(axis=1)
-    homogenised.varnames = list(homogenised.values.columns)
-    homogenised.values['clim'] = homog
+    arr = obs.values.values.astype(np.float64)
+    names = list(obs.values.columns)
+    # placeholders of optional statistics are columns holding NaN
+    # (dropna(axis=1), homog.py:212); assemble the frame in one go
+    keep = ~np.isnan(arr).any(axis=0)
+    cols = {}
+    for i, nm in enumerate(names):
+        if keep[i]:
+            cols[nm] = arr[:, i]
+    cols['clim'] = np.asarray(homog, dtype=np.float64)
+    varnames = list(cols)
+    nvars = obs.nvars
+
+    def add_var(values, varname):            # PointSet.add_var (grid.py:109-130)
+        if varname in varnames:
+            varname += '_new'
+        varnames.append(varname)
+        cols[varname] = np.asarray(values, dtype=np.float64)
+
     if flag:
-        homogenised.add_var(flagcol, 'Flag')
+        add_var(flagcol, 'Flag')
+        nvars += 1
     if optional_stats:
         for key, value in optional_stats.items():
             if value and key == 'lperc':
@@ -83,10 +98,15 @@ def _finish(obs, local, fixcols, method, skewness, hom_in, flag,
                 with np.errstate(invalid='ignore'):
                     pdet = np.where(filled >= med, local['rperc'].values,
                                     local['lperc'].values)
-                homogenised.add_var(varname='pdet', values=pdet)
+                add_var(pdet, 'pdet')
+                nvars += 1
             elif value:
                 name = _STATS_NAMES[key]
-                homogenised.add_var(varname=name, values=local[name].values)
+                add_var(local[name].values, name)
+                nvars += 1
+    homogenised = gr.PointSet(obs.name + '_homogenised', obs.nodata, nvars,
+                              varnames, pd.DataFrame(cols,
+                                                     index=obs.values.index))
     return homogenised, int(det)
 
 
@@ -154,7 +174,7 @@ def detect(grids, obs_file, rad=0, method='mean', prob=0.95, skewness=None,
 
 def detect_many(grids, obs_list, rad=0, method='mean', prob=0.95,
                 skewness=None, percentile=None, flag=True, header=True,
-                optional_stats=None):
+                optional_stats=None, stream=None):
     """Extension: ``detect`` for many candidate stations against ONE stack
     (the ``interface/simstats.py:204-209`` calling pattern) with one K2c and
     one K3 launch.  Returns a list of ``detect``-style tuples."""
@@ -162,10 +182,11 @@ def detect_many(grids, obs_list, rad=0, method='mean', prob=0.95,
     prepared = [_prepare_obs(o, grids, header) for o in obs_list]
     locs = [p[1] for p in prepared]
     locals_ = [ps.values for ps in
-               grids.stats_area_many(locs, rad, p=prob, **sel)]
+               grids.stats_area_many(locs, rad, p=prob, stream=stream, **sel)]
     if method == 'percentile' and percentile != prob:
         vperc = [ps.values for ps in
-                 grids.stats_area_many(locs, rad, lperc=True, p=percentile)]
+                 grids.stats_area_many(locs, rad, lperc=True, p=percentile,
+                                       stream=stream)]
     else:
         vperc = locals_
     S, dz = len(prepared), grids.dz
@@ -190,7 +211,7 @@ def detect_many(grids, obs_list, rad=0, method='mean', prob=0.95,
     filled, homog, flagcol, det = _capi.detect(
         *cols, method=method, thr=float(skewness or 0.0),
         nodata=prepared[0][0].nodata if prepared else -999.9,
-        device=grids.device)
+        device=grids.device, stream=stream)
     out = []
     for s, obs in enumerate(obs_filled):
         hom, dn = _finish(obs, locals_[s], None, method, skewness,
@@ -218,19 +239,25 @@ def fill_station(pset_file, values, time_min, time_max, time_step=1,
     frame = pset.values
     varcol = pset.varnames.index('clim')
     times = np.arange(time_min, time_max, time_step)
+    rows = frame.values.astype(np.float64)
     have = frame['time'].values
-    first = frame.iloc[0].values
-    filled = np.zeros((times.shape[0], frame.shape[1]))
+    ncol = rows.shape[1]
+    # a synthesised row: x, y of the first row, the time, the columns between
+    # `time` and `clim` of the first row (station id), then the fill value
+    template = np.concatenate([rows[0, :2], [0.0], rows[0, 3:varcol], [0.0]])
+    fillpos = 3 + max(varcol - 3, 0)
+    filled = np.zeros((times.shape[0], ncol))
     j = 0
     added = 0
+    nrows = have.shape[0]
     for i, t in enumerate(times):
-        if j < have.shape[0] and t == have[j]:
-            filled[i] = frame.iloc[j].values
+        if j < nrows and t == have[j]:
+            filled[i] = rows[j]
             j += 1
         else:
-            row = np.concatenate([first[:2], [t], first[3:varcol],
-                                  [values[i]]])
-            filled[i] = row[:frame.shape[1]]
+            template[2] = t
+            template[fillpos] = values[i]
+            filled[i] = template[:ncol]
             added += 1
     pset.values = pd.DataFrame(filled, columns=frame.columns)
     return pset, added

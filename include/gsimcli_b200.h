@@ -91,6 +91,10 @@ int gsb_stack_create(int device, int64_t R, int64_t N, gsb_stack** out);
 int gsb_stack_destroy(gsb_stack* s);
 int gsb_stack_info(const gsb_stack* s, int64_t* R, int64_t* N, int64_t* pitch,
                    int* device);
+/* tuning knobs.  "k2_sm_reserve" = number of SMs the full-grid kernel leaves
+ * free (default 0) so that station-column / detect launches on another stream
+ * run concurrently with it instead of queueing behind its persistent CTAs. */
+int gsb_stack_set_option(gsb_stack* s, const char* key, int64_t value);
 /* raw device pointer of row 0 (float32, row pitch `pitch` elements): the
  * tensor handle torch wraps for NCCL plumbing.  Never dereference on host. */
 int gsb_stack_device_ptr(const gsb_stack* s, void** dptr);
