@@ -1,0 +1,31 @@
+// k2_args.cuh -- launch arguments shared by the two full-grid K2 kernels
+// (k2_grid_sort.cu: register bitonic sort; k2_grid_csort.cu: counting sort)
+#pragma once
+#include "gsb_common.cuh"
+
+struct K2Args {
+    int R;
+    int nchunks;
+    int nplanes;
+    int lockstep;      // experiment knob: block barriers inside the sort (GSB_K2_LOCKSTEP)
+    int skew;          // warps 4..7 run the in-lane sort before the tile barrier (GSB_K2_SKEW)
+    float nodata;
+    long long ntiles;
+    long long n0;      // first column of tile 0 (multiple of 4: TMA needs 16-byte aligned boxes)
+    long long nn;      // columns from n0 to the end of the requested range
+    long long skip;    // leading columns of tile 0 that precede the requested range
+    float* out;        // plane 0, column n0 (may point `skip` elements before the buffer)
+    long long out_pitch;
+    unsigned char kind[GSB_MAX_PLANES];
+    double q[GSB_MAX_PLANES];
+};
+
+// per-warp scratch region of the counting-sort kernel, in 32-bit words:
+// left halo, NPAD slots + one padding word per IPT slots, overflow bin, right
+// halo; multiples of 4 so the region can be cleared with 16-byte stores
+#define K2_CS_LPAD(HALO) (((2 * (HALO)) + 3) & ~3)
+#define K2_CS_REGION_WORDS(IPT, HALO) \
+    ((K2_CS_LPAD(HALO) + (IPT) * 32 + 32 + 2 * (HALO) + 8 + 3) & ~3)
+
+int gsb_launch_k2_csort(gsb_stack* s, const K2Args& args, int ipt, int grid, bool mode,
+                        int halo, cudaStream_t st);

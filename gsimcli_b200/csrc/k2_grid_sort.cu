@@ -25,6 +25,7 @@
 // with binary lifting) and stores 4 adjacent nodes with one 16-byte store.
 // HBM traffic: the stack is read exactly once (4 B per node-realization).
 #include "gsb_common.cuh"
+#include "k2_args.cuh"
 #include <utility>
 #include <stdlib.h>
 
@@ -34,22 +35,6 @@ constexpr int K2_STAGE_BYTES = 4096;   // 32 rows x 32 nodes x 4 B
 constexpr int K2_NST = 32;             // ring depth: one full R=1024 tile
 constexpr unsigned FULL = 0xffffffffu;
 
-struct K2Args {
-    int R;
-    int nchunks;
-    int nplanes;
-    int lockstep;      // experiment knob: block barriers inside the sort (GSB_K2_LOCKSTEP)
-    int skew;          // warps 4..7 run the in-lane sort before the tile barrier (GSB_K2_SKEW)
-    float nodata;
-    long long ntiles;
-    long long n0;      // first column of tile 0 (multiple of 4: TMA needs 16-byte aligned boxes)
-    long long nn;      // columns from n0 to the end of the requested range
-    long long skip;    // leading columns of tile 0 that precede the requested range
-    float* out;        // plane 0, column n0 (may point `skip` elements before the buffer)
-    long long out_pitch;
-    unsigned char kind[GSB_MAX_PLANES];
-    double q[GSB_MAX_PLANES];
-};
 
 // ---------------------------------------------------------------------------
 // Batcher odd-even merge sort network for N = 2^k inputs, generated at compile
@@ -625,6 +610,14 @@ int gsb_launch_k2_sort(gsb_stack* s, const GsbPlanes& pl, float nodata, int64_t 
     const int ctas = s->sm_count - s->k2_sm_reserve;
     const int grid = static_cast<int>(args.ntiles < ctas ? args.ntiles : ctas);
     if (grid <= 0) return GSB_OK;
+    // counting-sort kernel for the deep columns (default for R > 128); the
+    // register bitonic sort below stays the kernel for shallow ones
+    const char* alg = getenv("GSB_K2_ALGO");
+    const bool want_cs = alg ? (strcmp(alg, "csort") == 0) : (ipt >= 32);
+    if (want_cs && ipt >= 8) {
+        const char* hl = getenv("GSB_K2_HALO");
+        return gsb_launch_k2_csort(s, args, ipt, grid, pl.need_mode != 0, hl ? atoi(hl) : 12, st);
+    }
     const char* cp = getenv("GSB_K2_CPW");
     const int cpw = cp ? atoi(cp) : 2;
     if (cpw == 2)

@@ -134,6 +134,65 @@ def test_grid_stats_all_R(R):
     check_grid(st)
 
 
+@pytest.mark.parametrize('algo', ['csort', 'bitonic'])
+@pytest.mark.parametrize('R', [100, 129, 200, 256, 500, 512, 1000, 1024])
+def test_grid_stats_both_sort_kernels(algo, R, monkeypatch):
+    """The counting-sort kernel (k2_grid_csort.cu) and the register bitonic
+    kernel (k2_grid_sort.cu) must both be exact; GSB_K2_ALGO forces one."""
+    monkeypatch.setenv('GSB_K2_ALGO', algo)
+    dims = [11, 9, 5]
+    st = synth.stack(2000 + R, R, dims)
+    st[:, 3] = 812.5
+    st[:, 4] = np.float32(ND)
+    st[:, 5] = np.float32(ND)
+    st[R // 2, 5] = 640.25
+    st[:, 8] = np.where(np.arange(R) % 2 == 0, 500.0, 600.0)
+    check_grid(st)
+
+
+@pytest.mark.parametrize('algo', ['csort', 'bitonic'])
+def test_grid_stats_adversarial_distributions(algo, monkeypatch):
+    """Distributions that defeat a linear bin map (outliers, clusters, huge
+    offsets, heavy ties, first realizations all missing) must stay exact."""
+    monkeypatch.setenv('GSB_K2_ALGO', algo)
+    rng = np.random.default_rng(17)
+    for R in (200, 1000):
+        N = 160
+        st = np.round(rng.normal(800.0, 150.0, size=(R, N)) * 16) / 16
+        st[0, 0:8] = 3.0e30                       # one huge outlier: every other value in one bin
+        st[1, 8:16] = -3.0e30
+        st[:, 16:24] = np.round(rng.normal(0, 1, size=(R, 8)) * 4) / 4 + np.where(
+            rng.uniform(size=(R, 8)) < 0.5, -1.0e6, 1.0e6)        # two far clusters
+        st[:, 24:32] = 1.0e7 + np.round(rng.uniform(0, 8, size=(R, 8)) * 16) / 16   # big offset, tiny range
+        st[:, 32:40] = np.round(rng.exponential(50.0, size=(R, 8)) * 16) / 16 - 200.0   # negative + heavy tail
+        st[:, 40:48] = rng.integers(0, 3, size=(R, 8)) * 0.5       # three atoms
+        st[:, 48:56] = np.where(rng.uniform(size=(R, 8)) < 0.7, 0.0,
+                                np.round(rng.gamma(2.0, 20.0, size=(R, 8)) * 16) / 16)   # zero-inflated
+        st[:40, 56:64] = ND                        # first realizations all missing
+        st[:, 64:72] = -np.abs(st[:, 64:72])       # all negative
+        st[:40, 72:80] = ND
+        st[:, 72:80] = -np.abs(st[:, 72:80])       # all negative AND no pivot in the first rows
+        st[rng.uniform(size=st.shape) < 0.01] = ND
+        st[:, 80] = np.float32(3.4e38)
+        st[::2, 80] = np.float32(-3.4e38)          # range overflows float32
+        st[:, 81] = np.float32(1e-42)
+        st[::3, 81] = np.float32(3e-42)            # subnormal range
+        st32 = st.astype(np.float32)
+        R_, N_ = st32.shape
+        stack = _capi.Stack(R_, N_)
+        stack.upload(st32)
+        flags = _capi.MEDIAN | _capi.PERC | _capi.MODE
+        out = stack.stats_grid(flags, 0.95, QS, ND)
+        stack.close()
+        ref = O.grid_stats(st32, ND, flags, 0.95, QS)
+        same_bits(out[0], ref['medianmap'])
+        same_bits(out[1], ref['percmap'][:, 0])
+        same_bits(out[2], ref['percmap'][:, 1])
+        for i in range(len(QS)):
+            same_bits(out[3 + i], ref['percentiles'][:, i])
+        same_bits(out[3 + len(QS)], ref['modemap'])
+
+
 def test_grid_stats_subrange_and_no_mode():
     st = synth.stack(5, 200, [20, 10, 4])
     check_grid(st, p=0.9, percentiles=[0.0, 0.5, 1.0, 0.333], mode=False,
