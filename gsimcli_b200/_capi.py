@@ -75,6 +75,7 @@ SIGNATURES = {
     'gsb_detect': (C.c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, C.c_int,
                              C.c_int, C.c_int, C.c_double, C.c_double, c_vp,
                              c_vp, c_vp, c_vp, C.c_int, C.c_int, c_vp]),
+    'gsb_debug_cs_counters': (C.c_int, [c_vp, C.c_int]),
 }
 
 

@@ -31,6 +31,10 @@
 #include "gsb_common.cuh"
 #include "k2_args.cuh"
 
+// [0] columns, [1] columns with big bins, [2] columns on the generic path,
+// [3] sum of odd-even phases, [4] big bins sorted, [5] values in big bins
+__device__ unsigned long long gsb_cs_counters[8];
+
 namespace {
 
 constexpr unsigned FULL = 0xffffffffu;
@@ -65,6 +69,22 @@ __device__ __forceinline__ float cs_sanitize(float x, float nodata) {
     return r;
 }
 
+__device__ __forceinline__ uint64_t cs_pack2(float a, float b) {
+    uint64_t r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b));
+    return r;
+}
+__device__ __forceinline__ float cs_lo2(uint64_t v) {
+    float a, b;
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v));
+    return a;
+}
+__device__ __forceinline__ float cs_hi2(uint64_t v) {
+    float a, b;
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v));
+    return b;
+}
+
 // B(p) = A(p - s) over the NPAD-bit string distributed IPT bits per lane
 template <int IPT>
 __device__ __forceinline__ uint32_t cs_bits_shift(uint32_t A, int s, int lane) {
@@ -85,7 +105,10 @@ k2_csort_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant_
     constexpr int NPAD = IPT * 32;
     constexpr int LOGI = CLog2<IPT>::v;
     constexpr int LOGN = LOGI + 5;
-    constexpr int B = NPAD;                       // bins (+1 overflow bin for missing values)
+    // bins: every word of the slot region doubles as a histogram bin, padding
+    // words included, so lane l owns the IPT+1 bins [l*(IPT+1), (l+1)*(IPT+1))
+    // and bin b simply lives at word b; word B is the bin of the missing values
+    constexpr int B = 32 * (IPT + 1);
     constexpr int W = IPT + 2 * HALO;             // window registers per lane
     constexpr int LPAD = K2_CS_LPAD(HALO);
     constexpr int REG_WORDS = K2_CS_REGION_WORDS(IPT, HALO);
@@ -95,6 +118,7 @@ k2_csort_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant_
     uint32_t* scratch_all = reinterpret_cast<uint32_t*>(smem + TILE_BYTES);
     float* cstat_all = reinterpret_cast<float*>(scratch_all + CS_WARPS * REG_WORDS);
     uint64_t* full = reinterpret_cast<uint64_t*>(cstat_all + CS_WARPS * 8);
+    uint32_t* readers = reinterpret_cast<uint32_t*>(full + 1);
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -115,10 +139,10 @@ k2_csort_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant_
     // banks distinct)
     float* A = reinterpret_cast<float*>(scratch_all + warp * REG_WORDS + LPAD);
     uint32_t* H = reinterpret_cast<uint32_t*>(A);
-    float* cstat = cstat_all + warp * 8;
     auto idx = [](int p) { return p + (p >> LOGI); };
 
     if (threadIdx.x == 0) {
+        *readers = 0u;
         gsb_mbar_init(full, 1);
         gsb_fence_barrier_init();
         gsb_prefetch_tmap(&tmap);
@@ -129,8 +153,8 @@ k2_csort_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant_
     for (int i = lane; i < REG_WORDS - LPAD; i += 32) H[i] = 0u;
     __syncthreads();
 
-    // bytes of this lane's 8 bytes (nodes 2w, 2w+1 of row `lane`) inside a
-    // 32-row chunk, 128-byte TMA swizzle applied
+    // byte offset of node 2w of row `lane` inside a 32-row chunk, 128-byte TMA
+    // swizzle applied (node 2w+1 is the next float)
     const uint32_t my_off = lane * 128u
         + (((static_cast<uint32_t>(warp) >> 1) ^ (lane & 7u)) << 4) + (warp & 1u) * 8u;
 
@@ -151,99 +175,89 @@ k2_csort_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant_
         gsb_mbar_wait(full, phase);
         phase ^= 1u;
 
-        // ---- tile -> registers, nodata/NaN/padding -> +INF
-        float xs[IPT], xs1[IPT];
-#pragma unroll
-        for (int j = 0; j < IPT; ++j) {
-            if (j < a.nchunks) {
-                const float2 t = *reinterpret_cast<const float2*>(smem + j * 4096 + my_off);
-                xs[j] = cs_sanitize(t.x, a.nodata);
-                xs1[j] = cs_sanitize(t.y, a.nodata);
-            } else {
-                xs[j] = INF;
-                xs1[j] = INF;
-            }
-        }
-        // tile consumed: stream the next one in behind the compute
-        __syncthreads();
-        if (threadIdx.x == 0) {
-            const long long nxt = tile + gridDim.x;
-            if (nxt < a.ntiles) issue_tile(nxt);
-        }
-
-        // ---- pass 0: pivot, shifted moments, min / max of both columns
-        float piv[2], S1[2], S2[2], S3[2], mn[2], mx[2];
-        int have_piv[2];
-#pragma unroll
-        for (int c = 0; c < 2; ++c) {
-            // pivot: the valid value among the first 32 realizations closest to
-            // their mean (an actual element: the max below may then use it
-            // as the stand-in for missing values)
-            const float x0 = c == 0 ? xs[0] : xs1[0];
-            const bool ok = x0 < INF;
-            const float s0 = cs_warp_sum(ok ? x0 : 0.f);
-            const int c0 = __reduce_add_sync(FULL, ok ? 1 : 0);
-            const float m0 = c0 ? s0 / static_cast<float>(c0) : 0.f;
-            float dist = ok ? fabsf(x0 - m0) : INF;
-            float cand = ok ? x0 : 0.f;
-#pragma unroll
-            for (int o = 16; o >= 1; o >>= 1) {
-                const float od = __shfl_xor_sync(FULL, dist, o);
-                const float oc = __shfl_xor_sync(FULL, cand, o);
-                if (od < dist || (od == dist && oc < cand)) { dist = od; cand = oc; }
-            }
-            piv[c] = c0 ? cand : 0.f;
-            have_piv[c] = c0;
-            S1[c] = S2[c] = S3[c] = 0.f;
-            mn[c] = INF;
-            mx[c] = c0 ? cand : -INF;
-        }
-#pragma unroll
-        for (int j = 0; j < IPT; ++j) {
-#pragma unroll
-            for (int c = 0; c < 2; ++c) {
-                const float x = c == 0 ? xs[j] : xs1[j];
-                const bool ok = x < INF;
-                const float xm = ok ? x : piv[c];
-                mn[c] = fminf(mn[c], x);
-                mx[c] = fmaxf(mx[c], xm);        // piv is an element: a valid stand-in
-                const float d = xm - piv[c];
-                const float d2 = d * d;
-                S1[c] += d;
-                S2[c] += d2;
-                S3[c] = fmaf(d2, d, S3[c]);
-            }
-        }
-#pragma unroll
-        for (int c = 0; c < 2; ++c) {
-            if (!have_piv[c]) {
-                // the first 32 realizations are all missing: the pivot (0) is not
-                // an element, take the maximum the slow way
-                float m = -INF;
-#pragma unroll
-                for (int j = 0; j < IPT; ++j) {
-                    const float x = c == 0 ? xs[j] : xs1[j];
-                    m = x < INF ? fmaxf(m, x) : m;
-                }
-                mx[c] = m;
-            }
-            S1[c] = cs_warp_sum(S1[c]);
-            S2[c] = cs_warp_sum(S2[c]);
-            S3[c] = cs_warp_sum(S3[c]);
-            mn[c] = cs_warp_min(mn[c]);
-            mx[c] = cs_warp_max(mx[c]);
-        }
-
         const long long colbase = tile * 32 + warp * 2;
 #pragma unroll 1
         for (int c = 0; c < 2; ++c) {
-            if (c == 1) {
+            // ---- column 2w+c of the tile -> registers, nodata/NaN/padding -> +INF.
+            // One column at a time keeps the register file free of the other one;
+            // the tile is handed back to TMA once every warp has read its second
+            // column, and the refill overlaps that column's processing.
+            float xs[IPT];
+            {
+                const unsigned char* tp = smem + my_off + c * 4;
+                if (a.nchunks == IPT) {
 #pragma unroll
-                for (int j = 0; j < IPT; ++j) xs[j] = xs1[j];
-                piv[0] = piv[1]; S1[0] = S1[1]; S2[0] = S2[1]; S3[0] = S3[1];
-                mn[0] = mn[1]; mx[0] = mx[1];
+                    for (int j = 0; j < IPT; ++j)
+                        xs[j] = cs_sanitize(*reinterpret_cast<const float*>(tp + j * 4096), a.nodata);
+                } else {
+#pragma unroll
+                    for (int j = 0; j < IPT; ++j)
+                        xs[j] = j < a.nchunks
+                            ? cs_sanitize(*reinterpret_cast<const float*>(tp + j * 4096), a.nodata) : INF;
+                }
             }
-            const float lo = mn[0], hi = mx[0];
+            if (c == 1) {
+                // the last warp to have read its second column hands the tile back
+                // to TMA: no block-wide barrier, warps drift freely (at most one
+                // tile apart, the `full` barrier holds the fast ones)
+                __syncwarp();
+                if (lane == 0) {
+                    __threadfence_block();
+                    if (atomicAdd(readers, 1u) == CS_WARPS - 1u) {
+                        *readers = 0u;
+                        const long long nxt = tile + gridDim.x;
+                        if (nxt < a.ntiles) issue_tile(nxt);
+                    }
+                }
+            }
+
+            // ---- pass 0: pivot, shifted moments (packed f32x2), min / max
+            // pivot of the shifted sums: the first valid value among the first 32
+            // realizations.  An actual element, so a constant column gives d == 0
+            // exactly and the max below may use it as the stand-in for missing
+            // values; within a few sigma of the mean, which is all the float32
+            // shifted sums need
+            float piv, S1, S2, S3, lo, hi;
+            {
+                const uint32_t okm = __ballot_sync(FULL, xs[0] < INF);
+                const bool have_piv = okm != 0u;
+                const float cand = __shfl_sync(FULL, xs[0], have_piv ? __ffs(okm) - 1 : 0);
+                piv = have_piv ? cand : 0.f;
+                float mn = INF, mx = have_piv ? cand : -INF;
+                uint64_t s1 = 0, s2 = 0, s3 = 0;
+                const uint64_t pp = cs_pack2(piv, piv);
+#pragma unroll
+                for (int j = 0; j < IPT; j += 2) {
+                    float xm[2];
+#pragma unroll
+                    for (int u = 0; u < 2; ++u) {
+                        const float x = xs[j + u];
+                        xm[u] = x < INF ? x : piv;
+                        mn = fminf(mn, x);
+                        mx = fmaxf(mx, xm[u]);       // piv is an element: a valid stand-in
+                    }
+                    uint64_t d, d2;
+                    const uint64_t xx = cs_pack2(xm[0], xm[1]);
+                    asm("sub.f32x2 %0, %1, %2;" : "=l"(d) : "l"(xx), "l"(pp));
+                    asm("mul.f32x2 %0, %1, %1;" : "=l"(d2) : "l"(d));
+                    asm("add.f32x2 %0, %0, %1;" : "+l"(s1) : "l"(d));
+                    asm("add.f32x2 %0, %0, %1;" : "+l"(s2) : "l"(d2));
+                    asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(s3) : "l"(d2), "l"(d));
+                }
+                if (!have_piv) {
+                    // the first 32 realizations are all missing: the pivot (0) is
+                    // not an element, take the maximum the slow way
+                    float m = -INF;
+#pragma unroll
+                    for (int j = 0; j < IPT; ++j) m = xs[j] < INF ? fmaxf(m, xs[j]) : m;
+                    mx = m;
+                }
+                S1 = cs_warp_sum(cs_lo2(s1) + cs_hi2(s1));
+                S2 = cs_warp_sum(cs_lo2(s2) + cs_hi2(s2));
+                S3 = cs_warp_sum(cs_lo2(s3) + cs_hi2(s3));
+                lo = cs_warp_min(mn);
+                hi = cs_warp_max(mx);
+            }
             // ---- pass 1: histogram; the ATOMS result is the arrival index.
             // bin = round((x - lo) * scale) + 1 in [1, B-3]; the column extremes
             // get bins of their own (0 and B-2): DSS clamps to [datamin, datamax]
@@ -261,25 +275,34 @@ k2_csort_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant_
                 t += (x == hi) ? 1.0f : 0.0f;
                 t -= (x == lo) ? 1.0f : 0.0f;
                 const int b = __viaddmin_s32_relu(__float_as_int(t), -0x4B000000, B);
-                const uint32_t addr = hbase + static_cast<uint32_t>(idx(b)) * 4u;
+                const uint32_t addr = hbase + static_cast<uint32_t>(b) * 4u;
                 uint32_t old;
                 asm volatile("atom.shared.add.u32 %0, [%1], 1;" : "=r"(old) : "r"(addr) : "memory");
-                packed[j] = (old << 18) | addr;
+                packed[j] = old * 262144u + addr;
             }
             __syncwarp();
 
-            // ---- scan: lane l owns bins [l*IPT, (l+1)*IPT)
-            int nc, maxc;
+            // ---- scan: lane l owns bins [l*(IPT+1), (l+1)*(IPT+1))
+            // bins of more than HALO+1 values (rare: heavy ties away from the
+            // extremes, a dense spot of the distribution) are sorted one by one
+            // after the scatter; `maxc` is the largest of the others
+            int nc, maxc, n_lo, n_hi;
+            uint32_t big_start = 0, big_cnt = 0, nbig = 0;
+            bool generic = false;
+            uint32_t bigmask = 0;
             {
-                uint32_t tot = 0, mc = 0;
-                volatile uint32_t* hp = H + lane * (IPT + 1);
+                uint32_t* hp = H + lane * (IPT + 1);
+                uint32_t cnt[IPT + 1];
 #pragma unroll
-                for (int i = 0; i < IPT; ++i) {
-                    const uint32_t cn = hp[i];
-                    tot += cn;
+                for (int i = 0; i <= IPT; ++i) cnt[i] = hp[i];
+                uint32_t tot = 0, mc = 0;
+#pragma unroll
+                for (int i = 0; i <= IPT; ++i) {
+                    tot += cnt[i];
                     // the two atom bins hold equal values only: nothing to sort
-                    const bool atom = (i == 0 && lane == 0) || (i == IPT - 2 && lane == 31);
-                    mc = max(mc, atom ? 0u : cn);
+                    if (i == 0) mc = max(mc, lane == 0 ? 0u : cnt[i]);
+                    else if (i == IPT - 1) mc = max(mc, lane == 31 ? 0u : cnt[i]);
+                    else mc = max(mc, cnt[i]);
                 }
                 uint32_t incl = tot;
 #pragma unroll
@@ -289,37 +312,68 @@ k2_csort_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant_
                 }
                 nc = static_cast<int>(__shfl_sync(FULL, incl, 31));
                 maxc = static_cast<int>(__reduce_max_sync(FULL, mc));
+                n_lo = static_cast<int>(__shfl_sync(FULL, cnt[0], 0));
+                n_hi = static_cast<int>(__shfl_sync(FULL, cnt[IPT - 1], 31));
                 uint32_t run = incl - tot;
+                if (maxc <= HALO + 1) {
 #pragma unroll
-                for (int i = 0; i < IPT; ++i) { const uint32_t cn = hp[i]; hp[i] = run; run += cn; }
-                if (lane == 0) H[idx(B)] = static_cast<uint32_t>(nc);   // missing values go last
+                    for (int i = 0; i <= IPT; ++i) { hp[i] = run; run += cnt[i]; }
+                } else {
+                    // rare: remember this lane's big bins; `maxc` becomes the
+                    // largest of the small ones
+                    mc = 0;
+#pragma unroll
+                    for (int i = 0; i <= IPT; ++i) {
+                        const uint32_t cn = cnt[i];
+                        hp[i] = run;
+                        const bool atom = (i == 0 && lane == 0) || (i == IPT - 1 && lane == 31);
+                        if (!atom) {
+                            if (cn > HALO + 1) { big_start = run; big_cnt = cn; ++nbig; }
+                            else mc = max(mc, cn);
+                        }
+                        run += cn;
+                    }
+                    maxc = static_cast<int>(__reduce_max_sync(FULL, mc));
+                    // more than one big bin in a lane, or a very big one: generic sort
+                    generic = __any_sync(FULL, nbig > 1u || big_cnt > 128u);
+                    bigmask = __ballot_sync(FULL, nbig != 0u);
+                }
+                if (lane == 0) H[B] = static_cast<uint32_t>(nc);   // missing values go last
             }
             __syncwarp();
 
-            // ---- moment finals in float64 (lane 0), parked for the plane lanes
-            if (lane == 0) {
+            if (a.lockstep && lane == 0) {     // GSB_K2_LOCKSTEP doubles as the statistics switch
+                atomicAdd(&gsb_cs_counters[0], 1ull);
+                if (bigmask) atomicAdd(&gsb_cs_counters[1], 1ull);
+                if (generic) atomicAdd(&gsb_cs_counters[2], 1ull);
+                atomicAdd(&gsb_cs_counters[3], (unsigned long long)maxc);
+                atomicAdd(&gsb_cs_counters[4], (unsigned long long)__popc(bigmask));
+            }
+            // ---- moment finals: warp-uniform, every lane computes them (no
+            // shared-memory round trip); the two sums with cancellation in
+            // float64, divisions and roots in float32 (1e-7 relative)
+            float st_mean, st_var, st_sd, st_cv, st_skew;
+            {
                 const float fnan = __int_as_float(0x7fc00000);
-                const double dn = static_cast<double>(nc);
-                const double d1 = static_cast<double>(S1[0]), d2 = static_cast<double>(S2[0]);
-                const double delta = d1 / dn;
-                const double mean = static_cast<double>(piv[0]) + delta;
-                const bool constant = (S2[0] == 0.f);
-                const double m2 = constant ? 0.0 : fmax(d2 - d1 * delta, 0.0);
-                const double m3 = constant ? 0.0
-                    : static_cast<double>(S3[0]) - 3.0 * delta * d2 + 2.0 * dn * delta * delta * delta;
-                const double var = m2 / (dn - 1.0);
-                const double sd = sqrt(var);
-                cstat[0] = __int_as_float(nc);
-                cstat[1] = nc > 0 ? static_cast<float>(mean) : fnan;
-                cstat[2] = nc > 1 ? static_cast<float>(var) : fnan;
-                cstat[3] = nc > 1 ? static_cast<float>(sd) : fnan;
-                cstat[4] = nc > 1 ? static_cast<float>(sd / mean * 100.0) : fnan;
-                cstat[5] = nc < 3 ? fnan
-                         : (m2 == 0.0) ? 0.f
-                         : static_cast<float>((dn * sqrt(dn - 1.0) / (dn - 2.0)) * (m3 / (m2 * sqrt(m2))));
+                const float fn = static_cast<float>(nc);
+                const double d1 = static_cast<double>(S1), d2 = static_cast<double>(S2);
+                const float delta = S1 / fn;
+                const double dd = static_cast<double>(delta);
+                const bool constant = (S2 == 0.f);
+                const float m2 = constant ? 0.f : fmaxf(static_cast<float>(d2 - d1 * dd), 0.f);
+                const float m3 = constant ? 0.f : static_cast<float>(
+                    static_cast<double>(S3) - 3.0 * dd * d2 + 2.0 * d1 * dd * dd);
+                const float mean = piv + delta;
+                const float var = m2 / (fn - 1.f);
+                const float sd = sqrtf(var);
+                st_mean = nc > 0 ? mean : fnan;
+                st_var = nc > 1 ? var : fnan;
+                st_sd = nc > 1 ? sd : fnan;
+                st_cv = nc > 1 ? sd / mean * 100.f : fnan;
+                const float r2 = rsqrtf(m2);
+                st_skew = nc < 3 ? fnan : (m2 == 0.f) ? 0.f
+                        : (fn * sqrtf(fn - 1.f) / (fn - 2.f)) * (m3 * r2 * r2 * r2);
             }
-
-            __syncwarp();
             const bool allsame = !(lo < hi);     // constant or empty column: nothing to sort
             float w[W];
             if (!allsame) {
@@ -331,12 +385,12 @@ k2_csort_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant_
                     packed[j] = p + (packed[j] >> 18);
                 }
                 __syncwarp();
-                if (lane < HALO) A[idx(NPAD + lane)] = INF;          // right halo
+                if (lane < HALO) A[idx(NPAD + lane)] = INF;          // right halo (word B was the overflow bin)
 #pragma unroll
                 for (int j = 0; j < IPT; ++j) A[idx(static_cast<int>(packed[j]))] = xs[j];
                 __syncwarp();
 
-                if (maxc > HALO + 1) {
+                if (generic) {
                     // ---- generic path: bitonic sort of the slot array in shared memory
 #pragma unroll 1
                     for (int k = 2; k <= NPAD; k <<= 1)
@@ -354,6 +408,33 @@ k2_csort_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant_
 #pragma unroll
                     for (int j = 0; j < IPT; ++j) w[HALO + j] = A[lane * (IPT + 1) + j];
                 } else {
+                    // ---- big bins: rank sort, the warp on one bin at a time
+#pragma unroll 1
+                    for (uint32_t bm = bigmask; bm != 0u; bm &= bm - 1u) {
+                        const int src = __ffs(bm) - 1;
+                        const int s0 = static_cast<int>(__shfl_sync(FULL, big_start, src));
+                        const int cn = static_cast<int>(__shfl_sync(FULL, big_cnt, src));
+                        float mine[4];
+                        int rank[4];
+#pragma unroll
+                        for (int m = 0; m < 4; ++m) {
+                            const int i = lane + 32 * m;
+                            mine[m] = i < cn ? A[idx(s0 + i)] : INF;
+                            rank[m] = 0;
+                        }
+#pragma unroll 1
+                        for (int jx = 0; jx < cn; ++jx) {
+                            const float y = A[idx(s0 + jx)];
+#pragma unroll
+                            for (int m = 0; m < 4; ++m)
+                                rank[m] += (y < mine[m] || (y == mine[m] && jx < lane + 32 * m)) ? 1 : 0;
+                        }
+                        __syncwarp();
+#pragma unroll
+                        for (int m = 0; m < 4; ++m)
+                            if (lane + 32 * m < cn) A[idx(s0 + rank[m])] = mine[m];
+                        __syncwarp();
+                    }
                     // ---- windows: [l*IPT - HALO, (l+1)*IPT + HALO) -> registers
                     const float* wp = A + lane * (IPT + 1);
 #pragma unroll
@@ -364,13 +445,14 @@ k2_csort_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant_
                     }
                     // max-bin-size phases of odd-even transposition
 #pragma unroll 1
-                    for (int ph = 0; ph < maxc && maxc > 1; ph += 2) {
+                    for (int ph = maxc > 1 ? maxc : 0; ph > 0; ph -= 2) {
 #pragma unroll
                         for (int j = 0; j + 1 < W; j += 2) {
                             const float x = w[j], y = w[j + 1];
                             w[j] = fminf(x, y);
                             w[j + 1] = fmaxf(x, y);
                         }
+                        if (ph == 1) break;
 #pragma unroll
                         for (int j = 1; j + 1 < W; j += 2) {
                             const float x = w[j], y = w[j + 1];
@@ -403,35 +485,73 @@ k2_csort_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant_
                     const int mloc = nc - lane * IPT;
                     if (mloc <= 0) M = 0;
                     else if (mloc < IPT) M &= (1u << mloc) - 1u;
-                    uint32_t P[LOGN + 1];
-                    P[0] = M;
-                    int top = __any_sync(FULL, M != 0) ? 0 : -1;
+                    int pe = 0, best = 1;
+                    if (generic) {
+                        // generic path: runs of any length, binary lifting
+                        uint32_t P[LOGN + 1];
+                        P[0] = M;
+                        int top = __any_sync(FULL, M != 0) ? 0 : -1;
 #pragma unroll
-                    for (int i = 0; i < LOGN; ++i) {
-                        P[i + 1] = 0;
-                        if (top == i) {
-                            const uint32_t nx = P[i] & cs_bits_shift<IPT>(P[i], 1 << i, lane);
-                            if (__any_sync(FULL, nx != 0)) { P[i + 1] = nx; top = i + 1; }
+                        for (int i = 0; i < LOGN; ++i) {
+                            P[i + 1] = 0;
+                            if (top == i) {
+                                const uint32_t nx = P[i] & cs_bits_shift<IPT>(P[i], 1 << i, lane);
+                                if (__any_sync(FULL, nx != 0)) { P[i + 1] = nx; top = i + 1; }
+                            }
                         }
-                    }
-                    uint32_t cur = 0;
-                    int len = 0;
+                        uint32_t cur = 0;
+                        int len = 0;
 #pragma unroll
-                    for (int i = LOGN; i >= 0; --i) {
-                        if (i == top) { cur = P[i]; len = 1 << i; }
-                        else if (i < top) {
-                            const uint32_t cand = cur & cs_bits_shift<IPT>(P[i], len, lane);
-                            if (__any_sync(FULL, cand != 0)) { cur = cand; len += 1 << i; }
+                        for (int i = LOGN; i >= 0; --i) {
+                            if (i == top) { cur = P[i]; len = 1 << i; }
+                            else if (i < top) {
+                                const uint32_t cand = cur & cs_bits_shift<IPT>(P[i], len, lane);
+                                if (__any_sync(FULL, cand != 0)) { cur = cand; len += 1 << i; }
+                            }
                         }
+                        if (top >= 0) {
+                            const uint32_t bl = __ballot_sync(FULL, cur != 0);
+                            const int lf = __ffs(bl) - 1;
+                            const uint32_t wd = __shfl_sync(FULL, cur, lf);
+                            pe = lf * IPT + __ffs(wd) - 1;
+                        }
+                        modev = A[idx(pe)];
+                    } else {
+                        // window path: the extremes sit in their own bins, so
+                        // their multiplicities are the bin counts; every other
+                        // run is at most maxc long -- grow it one step at a time.
+                        // Keep only bits of the regular positions (n_lo, nc - n_hi)
+                        {
+                            const int a0 = n_lo + 1 - lane * IPT;      // first kept bit
+                            const int a1 = nc - n_hi - lane * IPT;     // first dropped bit
+                            uint32_t keep = 0xffffffffu;
+                            if (a0 >= 32) keep = 0; else if (a0 > 0) keep &= ~((1u << a0) - 1u);
+                            if (a1 <= 0) keep = 0; else if (a1 < 32) keep &= (1u << a1) - 1u;
+                            M &= keep;
+                        }
+                        uint32_t cur = M;      // bit p: a run of >= 2 ends at p
+                        int k = 1;             // run length - 1 of the bits in `cur`
+                        if (__any_sync(FULL, cur != 0)) {
+#pragma unroll 1
+                            for (;;) {
+                                const uint32_t nx = cur & cs_bits_shift<IPT>(M, k, lane);
+                                if (!__any_sync(FULL, nx != 0)) break;
+                                cur = nx;
+                                ++k;
+                            }
+                            const uint32_t bl = __ballot_sync(FULL, cur != 0);
+                            const int lf = __ffs(bl) - 1;
+                            const uint32_t wd = __shfl_sync(FULL, cur, lf);
+                            pe = lf * IPT + __ffs(wd) - 1 - k;     // start of the first longest run
+                            best = k + 1;
+                        } else {
+                            pe = n_lo < nc ? n_lo : 0;             // all regular values distinct
+                        }
+                        // ties -> smallest value: lo atom, then regular, then hi atom
+                        modev = A[idx(pe)];
+                        if (n_lo >= best) { modev = lo; best = n_lo; }
+                        if (n_hi > best) modev = hi;
                     }
-                    int pe = 0;
-                    if (top >= 0) {
-                        const uint32_t bl = __ballot_sync(FULL, cur != 0);
-                        const int lf = __ffs(bl) - 1;
-                        const uint32_t wd = __shfl_sync(FULL, cur, lf);
-                        pe = lf * IPT + __ffs(wd) - 1;
-                    }
-                    modev = A[idx(pe)];
                 }
             }
 
@@ -455,9 +575,10 @@ k2_csort_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant_
                     return static_cast<float>(r);
                 }
                 if (kind == GSB_PK_MODE) return modev;
-                float r = cstat[slot];
+                float r = slot == 1 ? st_mean : slot == 2 ? st_var : slot == 3 ? st_sd
+                        : slot == 4 ? st_cv : st_skew;
                 if (allsame && slot >= 2) {
-                    if (slot == 4) r = (nc > 1) ? 0.f / cstat[1] * 100.f : fnan;
+                    if (slot == 4) r = (nc > 1) ? 0.f / st_mean * 100.f : fnan;
                     else if (slot == 5) r = (nc >= 3) ? 0.f : fnan;
                     else r = (nc > 1) ? 0.f : fnan;
                 }
@@ -476,7 +597,7 @@ k2_csort_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant_
             // histogram back to zero for the next column
             {
                 float4* z = reinterpret_cast<float4*>(H);
-                for (int i = lane; i < (NPAD + 32 + 4) / 4; i += 32) z[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+                for (int i = lane; i < (B + 4) / 4; i += 32) z[i] = make_float4(0.f, 0.f, 0.f, 0.f);
             }
             __syncwarp();
         }
@@ -508,6 +629,15 @@ int cs_launch_ipt(gsb_stack* s, const K2Args& args, int ipt, int grid, cudaStrea
 }
 
 }  // namespace
+
+extern "C" int gsb_debug_cs_counters(unsigned long long* out, int reset) {
+    GSB_CUDA(cudaMemcpyFromSymbol(out, gsb_cs_counters, sizeof(unsigned long long) * 8));
+    if (reset) {
+        unsigned long long z[8] = {0};
+        GSB_CUDA(cudaMemcpyToSymbol(gsb_cs_counters, z, sizeof(z)));
+    }
+    return GSB_OK;
+}
 
 int gsb_launch_k2_csort(gsb_stack* s, const K2Args& args, int ipt, int grid, bool mode,
                         int halo, cudaStream_t st) {

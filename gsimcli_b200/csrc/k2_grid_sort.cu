@@ -613,10 +613,10 @@ int gsb_launch_k2_sort(gsb_stack* s, const GsbPlanes& pl, float nodata, int64_t 
     // counting-sort kernel for the deep columns (default for R > 128); the
     // register bitonic sort below stays the kernel for shallow ones
     const char* alg = getenv("GSB_K2_ALGO");
-    const bool want_cs = alg ? (strcmp(alg, "csort") == 0) : (ipt >= 32);
+    const bool want_cs = alg ? (strcmp(alg, "csort") == 0) : (ipt >= 8);
     if (want_cs && ipt >= 8) {
         const char* hl = getenv("GSB_K2_HALO");
-        return gsb_launch_k2_csort(s, args, ipt, grid, pl.need_mode != 0, hl ? atoi(hl) : 12, st);
+        return gsb_launch_k2_csort(s, args, ipt, grid, pl.need_mode != 0, hl ? atoi(hl) : 10, st);
     }
     const char* cp = getenv("GSB_K2_CPW");
     const int cpw = cp ? atoi(cp) : 2;

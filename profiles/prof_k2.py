@@ -39,4 +39,11 @@ for i in range(reps):
     gbs = (4.0 * R * N + 4.0 * npl * N) / ms / 1e6
     print('%s R=%d N=%d planes=%d: %.3f ms  %.1f GB/s  %.3e node-real/s' % (
         kind, R, N, npl, ms, gbs, R * N / ms * 1e3))
+if os.environ.get('GSB_K2_LOCKSTEP'):
+    import ctypes
+    buf = (ctypes.c_ulonglong * 8)()
+    _capi.lib().gsb_debug_cs_counters(buf, 1)
+    c = list(buf)
+    print('csort counters: columns %d, with big bins %d (%.3f%%), generic %d (%.3f%%), mean phases %.2f, big bins %d' % (
+        c[0], c[1], 100.0 * c[1] / max(c[0], 1), c[2], 100.0 * c[2] / max(c[0], 1), c[3] / max(c[0], 1), c[4]))
 print('checksum', float(torch.nan_to_num(out).double().sum()))
