@@ -61,6 +61,21 @@ def peaks():
     return 6650.0, 'fallback (B200_PROFILING.md)'
 
 
+def measured_traffic(r, nn):
+    """DRAM bytes per launch of the K2 kernel (dram__bytes_read.sum +
+    dram__bytes_write.sum) from the committed ``ncu --set full`` capture of
+    this very workload (profiles/k2_traffic.json), else None."""
+    path = os.path.join(ROOT, 'profiles', 'k2_traffic.json')
+    try:
+        with open(path) as fh:
+            for rec in json.load(fh):
+                if rec['R'] == r and rec['nodes'] == nn:
+                    return rec['dram_bytes_per_launch']
+    except (OSError, ValueError, KeyError):
+        pass
+    return None
+
+
 class ClockSampler(threading.Thread):
     """Samples nvidia-smi clocks / throttle reasons during the timed region."""
 
@@ -204,7 +219,7 @@ def run_gpu(args):
 
     def obs_list():
         return [gr.PointSet('cand%d' % i, ND, 5, list(cols),
-                            pd.DataFrame(s['obs'], columns=cols))
+                            np.array(s['obs'], dtype=np.float64))
                 for i, s in enumerate(stations)]
 
     # K2 runs on its own stream and leaves a few SMs free; the station path
@@ -328,7 +343,7 @@ def run_gpu(args):
             'gpu_launches': 3 * args.steps,
             'roofline': {'bound': 'hbm', 'achieved': achieved, 'peak': peak,
                          'unit': 'GB/s', 'frac': achieved / peak,
-                         'traffic': None, 'kernel': 'k2_sort_kernel',
+                         'traffic': measured_traffic(R, nn), 'kernel': 'k2_csort_kernel',
                          'kernel_ms': k_ms, 'algorithmic_bytes': alg_bytes,
                          'peak_source': peak_src},
             'cpu_baseline': {

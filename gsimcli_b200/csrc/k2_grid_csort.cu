@@ -119,6 +119,8 @@ k2_csort_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant_
     float* cstat_all = reinterpret_cast<float*>(scratch_all + CS_WARPS * REG_WORDS);
     uint64_t* full = reinterpret_cast<uint64_t*>(cstat_all + CS_WARPS * 8);
     uint32_t* readers = reinterpret_cast<uint32_t*>(full + 1);
+    double* ptab_q = reinterpret_cast<double*>(full + 2);
+    int* ptab_kind = reinterpret_cast<int*>(ptab_q + GSB_MAX_PLANES);
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -158,16 +160,19 @@ k2_csort_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant_
     const uint32_t my_off = lane * 128u
         + (((static_cast<uint32_t>(warp) >> 1) ^ (lane & 7u)) << 4) + (warp & 1u) * 8u;
 
-    // this lane's output planes (round r handles plane r*32 + lane)
-    int kind0 = -1, kind1 = -1;
-    double q0 = 0.0, q1 = 0.0;
-    if (lane < a.nplanes) { kind0 = a.kind[lane]; q0 = a.q[lane]; }
-    if (lane + 32 < a.nplanes) { kind1 = a.kind[lane + 32]; q1 = a.q[lane + 32]; }
+    // output planes: round r of a column handles plane r*32 + lane; the plane
+    // list (kind, moment slot, quantile) is parked in shared memory so that it
+    // costs no registers across the column loop
     auto slot_of = [](int kind) {
         return kind == GSB_PK_MEAN ? 1 : kind == GSB_PK_VAR ? 2 : kind == GSB_PK_STD ? 3
              : kind == GSB_PK_COEFVAR ? 4 : kind == GSB_PK_SKEW ? 5 : 1;
     };
-    const int slot0 = slot_of(kind0), slot1 = slot_of(kind1);
+    if (threadIdx.x < GSB_MAX_PLANES) {
+        const int k = threadIdx.x < a.nplanes ? a.kind[threadIdx.x] : -1;
+        ptab_q[threadIdx.x] = threadIdx.x < a.nplanes ? a.q[threadIdx.x] : 0.0;
+        ptab_kind[threadIdx.x] = (k < 0) ? -1 : (k | (slot_of(k) << 8));
+    }
+    __syncthreads();
     const uint32_t hbase = gsb_smem_u32(H);
 
     uint32_t phase = 0;
@@ -292,17 +297,22 @@ k2_csort_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant_
             uint32_t bigmask = 0;
             {
                 uint32_t* hp = H + lane * (IPT + 1);
-                uint32_t cnt[IPT + 1];
+                uint32_t tot = 0, mc = 0, c_first = 0, c_hi = 0;
 #pragma unroll
-                for (int i = 0; i <= IPT; ++i) cnt[i] = hp[i];
-                uint32_t tot = 0, mc = 0;
+                for (int i0 = 0; i0 <= IPT; i0 += 11) {
+                    uint32_t cnt[11];
 #pragma unroll
-                for (int i = 0; i <= IPT; ++i) {
-                    tot += cnt[i];
-                    // the two atom bins hold equal values only: nothing to sort
-                    if (i == 0) mc = max(mc, lane == 0 ? 0u : cnt[i]);
-                    else if (i == IPT - 1) mc = max(mc, lane == 31 ? 0u : cnt[i]);
-                    else mc = max(mc, cnt[i]);
+                    for (int u = 0; u < 11; ++u) if (i0 + u <= IPT) cnt[u] = hp[i0 + u];
+#pragma unroll
+                    for (int u = 0; u < 11; ++u) {
+                        const int i = i0 + u;
+                        if (i > IPT) continue;
+                        tot += cnt[u];
+                        // the two atom bins hold equal values only: nothing to sort
+                        if (i == 0) { c_first = cnt[u]; mc = max(mc, lane == 0 ? 0u : cnt[u]); }
+                        else if (i == IPT - 1) { c_hi = cnt[u]; mc = max(mc, lane == 31 ? 0u : cnt[u]); }
+                        else mc = max(mc, cnt[u]);
+                    }
                 }
                 uint32_t incl = tot;
 #pragma unroll
@@ -312,19 +322,26 @@ k2_csort_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant_
                 }
                 nc = static_cast<int>(__shfl_sync(FULL, incl, 31));
                 maxc = static_cast<int>(__reduce_max_sync(FULL, mc));
-                n_lo = static_cast<int>(__shfl_sync(FULL, cnt[0], 0));
-                n_hi = static_cast<int>(__shfl_sync(FULL, cnt[IPT - 1], 31));
+                n_lo = static_cast<int>(__shfl_sync(FULL, c_first, 0));
+                n_hi = static_cast<int>(__shfl_sync(FULL, c_hi, 31));
                 uint32_t run = incl - tot;
                 if (maxc <= HALO + 1) {
 #pragma unroll
-                    for (int i = 0; i <= IPT; ++i) { hp[i] = run; run += cnt[i]; }
+                    for (int i0 = 0; i0 <= IPT; i0 += 11) {
+                        uint32_t cnt[11];
+#pragma unroll
+                        for (int u = 0; u < 11; ++u) if (i0 + u <= IPT) cnt[u] = hp[i0 + u];
+#pragma unroll
+                        for (int u = 0; u < 11; ++u)
+                            if (i0 + u <= IPT) { hp[i0 + u] = run; run += cnt[u]; }
+                    }
                 } else {
                     // rare: remember this lane's big bins; `maxc` becomes the
                     // largest of the small ones
                     mc = 0;
-#pragma unroll
+#pragma unroll 1
                     for (int i = 0; i <= IPT; ++i) {
-                        const uint32_t cn = cnt[i];
+                        const uint32_t cn = hp[i];
                         hp[i] = run;
                         const bool atom = (i == 0 && lane == 0) || (i == IPT - 1 && lane == 31);
                         if (!atom) {
@@ -357,22 +374,22 @@ k2_csort_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant_
                 const float fnan = __int_as_float(0x7fc00000);
                 const float fn = static_cast<float>(nc);
                 const double d1 = static_cast<double>(S1), d2 = static_cast<double>(S2);
-                const float delta = S1 / fn;
+                const float delta = __fdividef(S1, fn);
                 const double dd = static_cast<double>(delta);
                 const bool constant = (S2 == 0.f);
                 const float m2 = constant ? 0.f : fmaxf(static_cast<float>(d2 - d1 * dd), 0.f);
                 const float m3 = constant ? 0.f : static_cast<float>(
                     static_cast<double>(S3) - 3.0 * dd * d2 + 2.0 * d1 * dd * dd);
                 const float mean = piv + delta;
-                const float var = m2 / (fn - 1.f);
+                const float var = __fdividef(m2, fn - 1.f);
                 const float sd = sqrtf(var);
                 st_mean = nc > 0 ? mean : fnan;
                 st_var = nc > 1 ? var : fnan;
                 st_sd = nc > 1 ? sd : fnan;
-                st_cv = nc > 1 ? sd / mean * 100.f : fnan;
+                st_cv = nc > 1 ? __fdividef(sd, mean) * 100.f : fnan;
                 const float r2 = rsqrtf(m2);
                 st_skew = nc < 3 ? fnan : (m2 == 0.f) ? 0.f
-                        : (fn * sqrtf(fn - 1.f) / (fn - 2.f)) * (m3 * r2 * r2 * r2);
+                        : __fdividef(fn * sqrtf(fn - 1.f), fn - 2.f) * (m3 * r2 * r2 * r2);
             }
             const bool allsame = !(lo < hi);     // constant or empty column: nothing to sort
             float w[W];
@@ -586,12 +603,12 @@ k2_csort_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant_
             };
             const long long col = colbase + c;
             if (col >= a.skip && col < a.nn) {
-                if (kind0 >= 0)
-                    a.out[static_cast<long long>(lane) * a.out_pitch + col] =
-                        plane_value(kind0, slot0, q0);
-                if (kind1 >= 0)
-                    a.out[static_cast<long long>(lane + 32) * a.out_pitch + col] =
-                        plane_value(kind1, slot1, q1);
+#pragma unroll 1
+                for (int pl = lane; pl < a.nplanes; pl += 32) {
+                    const int kk = ptab_kind[pl];
+                    a.out[static_cast<long long>(pl) * a.out_pitch + col] =
+                        plane_value(kk & 0xff, kk >> 8, ptab_q[pl]);
+                }
             }
             __syncwarp();
             // histogram back to zero for the next column
@@ -608,7 +625,8 @@ template <int IPT, bool MODE, int HALO>
 int cs_launch_one(gsb_stack* s, const K2Args& args, int grid, cudaStream_t st) {
     constexpr int NPAD = IPT * 32;
     const size_t smem = static_cast<size_t>(NPAD) * 128
-        + static_cast<size_t>(CS_WARPS) * K2_CS_REGION_WORDS(IPT, HALO) * 4 + CS_WARPS * 8 * 4 + 16;
+        + static_cast<size_t>(CS_WARPS) * K2_CS_REGION_WORDS(IPT, HALO) * 4 + CS_WARPS * 8 * 4 + 16
+        + GSB_MAX_PLANES * 12;
     auto kern = k2_csort_kernel<IPT, MODE, HALO>;
     GSB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   static_cast<int>(smem)));

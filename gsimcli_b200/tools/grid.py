@@ -47,6 +47,9 @@ class PointSet(object):
     def __init__(self, name=None, nodata=-999.9, nvars=0, varnames=None,
                  values=None, psetpath=None, header=True):
         self.path = psetpath
+        self._frame = None      # the DataFrame, once somebody asked for it
+        self._arr = None        # 2-D float64 rows while the frame is not built
+        self._index = None      # row index the frame will carry
         if self.path and os.path.isfile(self.path):
             self.load(self.path, nodata, header)
             return
@@ -56,9 +59,53 @@ class PointSet(object):
         self.varnames = varnames or []
         if values is None:
             values = np.zeros((0, 0))
-        self.values = pd.DataFrame(values)
-        if len(self.values.columns) == len(self.varnames):
-            self.values.columns = self.varnames
+        if isinstance(values, np.ndarray) and values.ndim == 2 \
+                and values.dtype.kind in 'fiu':
+            self._arr = values
+        else:
+            self.values = pd.DataFrame(values)
+            if len(self._frame.columns) == len(self.varnames):
+                self._frame.columns = self.varnames
+
+    # ``values`` is the reference's public attribute (a DataFrame,
+    # grid.py:99-104).  The hot path (detect_many: tens of point-sets per call)
+    # works on plain arrays; the frame is built the first time it is read.
+    @property
+    def values(self):
+        if self._frame is None:
+            arr = self._arr if self._arr is not None else np.zeros((0, 0))
+            frame = pd.DataFrame(arr, index=self._index)
+            if len(frame.columns) == len(self.varnames):
+                frame.columns = list(self.varnames)
+            self._frame, self._arr, self._index = frame, None, None
+        return self._frame
+
+    @values.setter
+    def values(self, frame):
+        self._frame, self._arr, self._index = frame, None, None
+
+    def array(self):
+        """The rows as a 2-D float64 array (no DataFrame is built)."""
+        if self._frame is not None:
+            return self._frame.values.astype(np.float64)
+        if self._arr is None:
+            return np.zeros((0, 0))
+        return self._arr.astype(np.float64)      # always a fresh copy
+
+    def columns(self):
+        """Column labels (those of the frame when it exists)."""
+        if self._frame is not None:
+            return list(self._frame.columns)
+        return list(self.varnames)
+
+    def row_index(self):
+        if self._frame is not None:
+            return self._frame.index
+        return self._index
+
+    def set_array(self, arr, index=None):
+        """Replace the rows by ``arr`` (columns = ``varnames``)."""
+        self._frame, self._arr, self._index = None, arr, index
 
     def __repr__(self):
         return str(self.values)

@@ -42,47 +42,65 @@ def _select_stats(method, skewness, optional_stats):
 
 def _prepare_obs(obs, grids, header):
     """Steps (2)-(5) of detect on one candidate: first valid coordinates,
-    Flag removal, nodata count and nodata -> NaN (homog.py:169-188)."""
+    Flag removal, nodata count and nodata -> NaN (homog.py:169-188).  Works on
+    the point-set's rows as an array: no DataFrame is touched."""
     if not isinstance(obs, gr.PointSet):
         path = obs
         obs = gr.PointSet()
         obs.load(path, header=header)
-    first = obs.values.index.get_loc(obs.values.first_valid_index())
-    obs_xy = [obs.values['x'].values[first], obs.values['y'].values[first]]
-    if 'Flag' in obs.values.columns:
-        obs.values = obs.values.drop('Flag', axis=1)
+    arr = obs.array()
+    names = obs.columns()
+    index = obs.row_index()
+    valid = ~np.isnan(arr).all(axis=1)
+    first = int(np.argmax(valid)) if valid.any() else 0
+    obs_xy = [arr[first, names.index('x')], arr[first, names.index('y')]]
+    if 'Flag' in names:
+        k = names.index('Flag')
+        arr = np.delete(arr, k, axis=1)
+        names.pop(k)
     if 'Flag' in obs.varnames:
         obs.varnames.remove('Flag')
         obs.nvars -= 1
-    nodatas = int(obs.values['clim'].isin([obs.nodata]).sum())
-    obs.values = obs.values.replace(obs.nodata, np.nan)
+    nodatas = int((arr[:, names.index('clim')] == obs.nodata).sum())
+    arr[arr == obs.nodata] = np.nan
+    obs.varnames = names
+    obs.set_array(arr, index)
     return obs, obs_xy, nodatas
+
+
+def _table(pset):
+    """{column name: 1-D array} view of a stats_area point-set."""
+    arr = pset.array()
+    return {nm: arr[:, i] for i, nm in enumerate(pset.columns())}
 
 
 def _finish(obs, local, fixcols, method, skewness, hom_in, flag,
             optional_stats, grids, obs_xy, rad):
     """Steps (7)-(12): K3 and assembly of the homogenised PointSet
-    (homog.py:204-269)."""
+    (homog.py:204-269).  ``local`` maps column names to arrays."""
     filled, homog, flagcol, det = hom_in
-    obs.values['clim'] = filled
-    arr = obs.values.values.astype(np.float64)
-    names = list(obs.values.columns)
+    arr = obs.array()
+    names = obs.columns()
+    arr[:, names.index('clim')] = filled
+    obs.set_array(arr, obs.row_index())
     # placeholders of optional statistics are columns holding NaN
-    # (dropna(axis=1), homog.py:212); assemble the frame in one go
+    # (dropna(axis=1), homog.py:212)
     keep = ~np.isnan(arr).any(axis=0)
-    cols = {}
-    for i, nm in enumerate(names):
-        if keep[i]:
-            cols[nm] = arr[:, i]
-    cols['clim'] = np.asarray(homog, dtype=np.float64)
-    varnames = list(cols)
+    varnames = [nm for i, nm in enumerate(names) if keep[i]]
+    cols = [arr[:, i] for i in range(len(names)) if keep[i]]
+    homog = np.asarray(homog, dtype=np.float64)
+    if 'clim' in varnames:
+        cols[varnames.index('clim')] = homog
+    else:
+        varnames.append('clim')
+        cols.append(homog)
     nvars = obs.nvars
 
     def add_var(values, varname):            # PointSet.add_var (grid.py:109-130)
         if varname in varnames:
             varname += '_new'
         varnames.append(varname)
-        cols[varname] = np.asarray(values, dtype=np.float64)
+        cols.append(np.asarray(values, dtype=np.float64))
 
     if flag:
         add_var(flagcol, 'Flag')
@@ -90,35 +108,34 @@ def _finish(obs, local, fixcols, method, skewness, hom_in, flag,
     if optional_stats:
         for key, value in optional_stats.items():
             if value and key == 'lperc':
-                if 'median' in local.columns:
-                    med = local['median'].values
+                if 'median' in local:
+                    med = local['median']
                 else:
-                    med = grids.stats_area(obs_xy, rad, lmed=True,
-                                           save=False).values['median'].values
+                    med = _table(grids.stats_area(obs_xy, rad, lmed=True,
+                                                  save=False))['median']
                 with np.errstate(invalid='ignore'):
-                    pdet = np.where(filled >= med, local['rperc'].values,
-                                    local['lperc'].values)
+                    pdet = np.where(filled >= med, local['rperc'],
+                                    local['lperc'])
                 add_var(pdet, 'pdet')
                 nvars += 1
             elif value:
                 name = _STATS_NAMES[key]
-                add_var(local[name].values, name)
+                add_var(local[name], name)
                 nvars += 1
     homogenised = gr.PointSet(obs.name + '_homogenised', obs.nodata, nvars,
-                              varnames, pd.DataFrame(cols,
-                                                     index=obs.values.index))
+                              varnames, np.column_stack(cols))
+    homogenised.set_array(homogenised.array(), obs.row_index())
     return homogenised, int(det)
 
 
 def _fix_columns(method, local, vline_perc):
     if method == 'mean':
-        return local['mean'].values, None, None
+        return local['mean'], None, None
     if method == 'median':
-        return local['median'].values, None, None
+        return local['median'], None, None
     if method == 'skewness':
-        return (local['median'].values, local['mean'].values,
-                local['skewness'].values)
-    return vline_perc['rperc'].values, vline_perc['lperc'].values, None
+        return local['median'], local['mean'], local['skewness']
+    return vline_perc['rperc'], vline_perc['lperc'], None
 
 
 def detect(grids, obs_file, rad=0, method='mean', prob=0.95, skewness=None,
@@ -142,25 +159,25 @@ def detect(grids, obs_file, rad=0, method='mean', prob=0.95, skewness=None,
     """
     sel = _select_stats(method, skewness, optional_stats)
     obs, obs_xy, nodatas = _prepare_obs(obs_file, grids, header)
-    local = grids.stats_area(obs_xy, rad, p=prob, save=save, **sel).values
+    local = _table(grids.stats_area(obs_xy, rad, p=prob, save=save, **sel))
 
-    meanvalues = local['mean'].values
+    meanvalues = local['mean']
     fn = 0
-    if obs.values.shape[0] < grids.dz:
+    if obs.array().shape[0] < grids.dz:
         obs, fn = fill_station(obs, meanvalues, grids.zi, grids.zi + grids.dz,
                                grids.cellz, header)
     if method == 'percentile' and percentile != prob:
         grids.reset_read()
-        vline_perc = grids.stats_area(obs_xy, rad, lperc=True, p=percentile,
-                                      save=False).values
+        vline_perc = _table(grids.stats_area(obs_xy, rad, lperc=True,
+                                             p=percentile, save=False))
     else:
         vline_perc = local
     fix_a, fix_b, fix_c = _fix_columns(method, local, vline_perc)
-    clim = obs.values['clim'].values.astype(np.float64)
+    clim = obs.array()[:, obs.columns().index('clim')]
     as2d = lambda a: None if a is None else np.asarray(a, np.float64)[None, :]
     filled, homog, flagcol, det = _capi.detect(
-        as2d(clim), as2d(meanvalues), as2d(local['lperc'].values),
-        as2d(local['rperc'].values), as2d(fix_a), as2d(fix_b), as2d(fix_c),
+        as2d(clim), as2d(meanvalues), as2d(local['lperc']),
+        as2d(local['rperc']), as2d(fix_a), as2d(fix_b), as2d(fix_c),
         method=method, thr=float(skewness or 0.0), nodata=obs.nodata,
         device=grids.device)
     homogenised, detected_number = _finish(
@@ -181,10 +198,10 @@ def detect_many(grids, obs_list, rad=0, method='mean', prob=0.95,
     sel = _select_stats(method, skewness, optional_stats)
     prepared = [_prepare_obs(o, grids, header) for o in obs_list]
     locs = [p[1] for p in prepared]
-    locals_ = [ps.values for ps in
+    locals_ = [_table(ps) for ps in
                grids.stats_area_many(locs, rad, p=prob, stream=stream, **sel)]
     if method == 'percentile' and percentile != prob:
-        vperc = [ps.values for ps in
+        vperc = [_table(ps) for ps in
                  grids.stats_area_many(locs, rad, lperc=True, p=percentile,
                                        stream=stream)]
     else:
@@ -195,16 +212,16 @@ def detect_many(grids, obs_list, rad=0, method='mean', prob=0.95,
     for s, (obs, _, _) in enumerate(prepared):
         local = locals_[s]
         fn = 0
-        if obs.values.shape[0] < dz:
-            obs, fn = fill_station(obs, local['mean'].values, grids.zi,
+        if obs.array().shape[0] < dz:
+            obs, fn = fill_station(obs, local['mean'], grids.zi,
                                    grids.zi + grids.dz, grids.cellz, header)
         fns.append(fn)
         obs_filled.append(obs)
         fa, fb, fc = _fix_columns(method, local, vperc[s])
-        cols[0][s] = obs.values['clim'].values
-        cols[1][s] = local['mean'].values
-        cols[2][s] = local['lperc'].values
-        cols[3][s] = local['rperc'].values
+        cols[0][s] = obs.array()[:, obs.columns().index('clim')]
+        cols[1][s] = local['mean']
+        cols[2][s] = local['lperc']
+        cols[3][s] = local['rperc']
         cols[4][s] = fa
         cols[5][s] = fa if fb is None else fb
         cols[6][s] = fa if fc is None else fc
@@ -236,11 +253,11 @@ def fill_station(pset_file, values, time_min, time_max, time_step=1,
     else:
         pset = gr.PointSet()
         pset.load(pset_file, header=header)
-    frame = pset.values
+    names = pset.columns()
     varcol = pset.varnames.index('clim')
     times = np.arange(time_min, time_max, time_step)
-    rows = frame.values.astype(np.float64)
-    have = frame['time'].values
+    rows = pset.array()
+    have = rows[:, names.index('time')]
     ncol = rows.shape[1]
     # a synthesised row: x, y of the first row, the time, the columns between
     # `time` and `clim` of the first row (station id), then the fill value
@@ -259,7 +276,8 @@ def fill_station(pset_file, values, time_min, time_max, time_step=1,
             template[fillpos] = values[i]
             filled[i] = template[:ncol]
             added += 1
-    pset.values = pd.DataFrame(filled, columns=frame.columns)
+    pset.varnames = names if len(names) == ncol else pset.varnames
+    pset.set_array(filled)
     return pset, added
 
 
