@@ -119,6 +119,7 @@ k2_csort_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant_
     float* cstat_all = reinterpret_cast<float*>(scratch_all + CS_WARPS * REG_WORDS);
     uint64_t* full = reinterpret_cast<uint64_t*>(cstat_all + CS_WARPS * 8);
     uint32_t* readers = reinterpret_cast<uint32_t*>(full + 1);
+    uint32_t* ticket = readers + 1;
     double* ptab_q = reinterpret_cast<double*>(full + 2);
     int* ptab_kind = reinterpret_cast<int*>(ptab_q + GSB_MAX_PLANES);
 
@@ -145,6 +146,7 @@ k2_csort_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant_
 
     if (threadIdx.x == 0) {
         *readers = 0u;
+        *ticket = 0u;
         gsb_mbar_init(full, 1);
         gsb_fence_barrier_init();
         gsb_prefetch_tmap(&tmap);
@@ -154,11 +156,6 @@ k2_csort_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant_
     for (int i = lane; i < LPAD; i += 32) A[-1 - i] = -INF;
     for (int i = lane; i < REG_WORDS - LPAD; i += 32) H[i] = 0u;
     __syncthreads();
-
-    // byte offset of node 2w of row `lane` inside a 32-row chunk, 128-byte TMA
-    // swizzle applied (node 2w+1 is the next float)
-    const uint32_t my_off = lane * 128u
-        + (((static_cast<uint32_t>(warp) >> 1) ^ (lane & 7u)) << 4) + (warp & 1u) * 8u;
 
     // output planes: round r of a column handles plane r*32 + lane; the plane
     // list (kind, moment slot, quantile) is parked in shared memory so that it
@@ -175,21 +172,30 @@ k2_csort_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant_
     __syncthreads();
     const uint32_t hbase = gsb_smem_u32(H);
 
-    uint32_t phase = 0;
-    for (long long tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x) {
-        gsb_mbar_wait(full, phase);
-        phase ^= 1u;
-
-        const long long colbase = tile * 32 + warp * 2;
-#pragma unroll 1
-        for (int c = 0; c < 2; ++c) {
-            // ---- column 2w+c of the tile -> registers, nodata/NaN/padding -> +INF.
-            // One column at a time keeps the register file free of the other one;
-            // the tile is handed back to TMA once every warp has read its second
-            // column, and the refill overlaps that column's processing.
+    // Columns are handed out one at a time from a CTA-wide ticket counter:
+    // ticket k is column k % 32 of the CTA's (k / 32)-th tile.  Warps therefore
+    // balance themselves (a column with heavy ties costs its warp one ticket,
+    // not the whole block a barrier), and the tile buffer goes back to TMA as
+    // soon as its 32 columns sit in registers -- about half a tile time before
+    // the last of them is finished.
+    for (;;) {
+        {
+            uint32_t tk = 0;
+            if (lane == 0) tk = atomicAdd(ticket, 1u);
+            tk = __shfl_sync(FULL, tk, 0);
+            const long long seq = tk >> 5;
+            const int c = static_cast<int>(tk & 31u);
+            const long long tile = blockIdx.x + seq * gridDim.x;
+            if (tile >= a.ntiles) break;
+            gsb_mbar_wait(full, static_cast<uint32_t>(seq & 1));
+            const long long col = tile * 32 + c;
+            // ---- column c of the tile -> registers, nodata/NaN/padding -> +INF
+            // (128-byte TMA swizzle: 16-byte chunk index ^ (row & 7))
+            const uint32_t my_off = lane * 128u
+                + (((static_cast<uint32_t>(c) >> 2) ^ (lane & 7u)) << 4) + (c & 3) * 4u;
             float xs[IPT];
             {
-                const unsigned char* tp = smem + my_off + c * 4;
+                const unsigned char* tp = smem + my_off;
                 if (a.nchunks == IPT) {
 #pragma unroll
                     for (int j = 0; j < IPT; ++j)
@@ -201,18 +207,15 @@ k2_csort_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant_
                             ? cs_sanitize(*reinterpret_cast<const float*>(tp + j * 4096), a.nodata) : INF;
                 }
             }
-            if (c == 1) {
-                // the last warp to have read its second column hands the tile back
-                // to TMA: no block-wide barrier, warps drift freely (at most one
-                // tile apart, the `full` barrier holds the fast ones)
-                __syncwarp();
-                if (lane == 0) {
-                    __threadfence_block();
-                    if (atomicAdd(readers, 1u) == CS_WARPS - 1u) {
-                        *readers = 0u;
-                        const long long nxt = tile + gridDim.x;
-                        if (nxt < a.ntiles) issue_tile(nxt);
-                    }
+            // the warp that loads the tile's last column hands the buffer back
+            // to TMA
+            __syncwarp();
+            if (lane == 0) {
+                __threadfence_block();
+                if (atomicAdd(readers, 1u) == 31u) {
+                    *readers = 0u;
+                    const long long nxt = tile + gridDim.x;
+                    if (nxt < a.ntiles) issue_tile(nxt);
                 }
             }
 
@@ -601,7 +604,6 @@ k2_csort_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant_
                 }
                 return r;
             };
-            const long long col = colbase + c;
             if (col >= a.skip && col < a.nn) {
 #pragma unroll 1
                 for (int pl = lane; pl < a.nplanes; pl += 32) {
