@@ -7,6 +7,7 @@
 #include <stdarg.h>
 #include <stdlib.h>
 #include <new>
+#include <mutex>
 
 static thread_local char g_err[512] = "";
 
@@ -473,31 +474,52 @@ int gsb_detect(const double* clim, const double* mean, const double* lperc, cons
     if (on_device)
         return gsb_launch_k3_detect(clim, mean, lperc, rperc, fix_a, fix_b, fix_c, S, dz, method,
                                     thr, nodata, filled, homog, flag, detected, st);
-    // host buffers: one staging allocation, 7 inputs + 3 outputs + counts
+    // host buffers: 7 inputs + 3 outputs + counts in one staging block that is
+    // kept per device (grow-only).  A stream-ordered cudaMallocAsync/cudaFreeAsync
+    // pair here returned its memory to the OS at the synchronize below, and that
+    // release waited for kernels running on OTHER streams (the persistent K2
+    // kernel): 7 ms per call instead of 0.1 ms.
     const size_t n = (size_t)S * dz, nb = n * 8;
-    char* d = nullptr;
-    GSB_CUDA(cudaMallocAsync((void**)&d, nb * 10 + (size_t)S * 4 + 64, st));
+    const size_t need = nb * 10 + (size_t)S * 4 + 64;
+    static std::mutex mu;
+    static void* cache_dev[64] = {nullptr};
+    static void* cache_pin[64] = {nullptr};
+    static size_t cache_bytes[64] = {0};
+    GSB_REQUIRE(device >= 0 && device < 64, "bad device %d", device);
+    std::lock_guard<std::mutex> lock(mu);
+    if (cache_bytes[device] < need) {
+        if (cache_dev[device]) cudaFree(cache_dev[device]);
+        if (cache_pin[device]) cudaFreeHost(cache_pin[device]);
+        cache_dev[device] = cache_pin[device] = nullptr;
+        cache_bytes[device] = 0;
+        const size_t cap = (need + 65535) & ~size_t(65535);
+        GSB_CUDA(cudaMalloc(&cache_dev[device], cap));
+        GSB_CUDA(cudaMallocHost(&cache_pin[device], cap));
+        cache_bytes[device] = cap;
+    }
+    char* d = (char*)cache_dev[device];
+    char* h = (char*)cache_pin[device];
     const double* hin[7] = {clim, mean, lperc, rperc, fix_a, fix_b ? fix_b : fix_a,
                             fix_c ? fix_c : fix_a};
     double* din[7];
     for (int i = 0; i < 7; ++i) {
         din[i] = (double*)(d + nb * i);
-        cudaMemcpyAsync(din[i], hin[i], nb, cudaMemcpyHostToDevice, st);
+        memcpy(h + nb * i, hin[i], nb);
     }
+    GSB_CUDA(cudaMemcpyAsync(d, h, nb * 7, cudaMemcpyHostToDevice, st));   // one pinned H2D
     double* dfilled = (double*)(d + nb * 7);
-    double* dhomog = (double*)(d + nb * 8);
-    double* dflag = (double*)(d + nb * 9);
     int32_t* ddet = (int32_t*)(d + nb * 10);
     int rc = gsb_launch_k3_detect(din[0], din[1], din[2], din[3], din[4], din[5], din[6], S, dz,
-                                  method, thr, nodata, dfilled, dhomog, dflag, ddet, st);
-    if (rc == GSB_OK) {
-        cudaMemcpyAsync(filled, dfilled, nb, cudaMemcpyDeviceToHost, st);
-        cudaMemcpyAsync(homog, dhomog, nb, cudaMemcpyDeviceToHost, st);
-        cudaMemcpyAsync(flag, dflag, nb, cudaMemcpyDeviceToHost, st);
-        cudaMemcpyAsync(detected, ddet, (size_t)S * 4, cudaMemcpyDeviceToHost, st);
-    }
-    cudaFreeAsync(d, st);
+                                  method, thr, nodata, dfilled, (double*)(d + nb * 8),
+                                  (double*)(d + nb * 9), ddet, st);
+    if (rc != GSB_OK) return rc;
+    // outputs are contiguous behind the inputs: one pinned D2H
+    GSB_CUDA(cudaMemcpyAsync(h + nb * 7, d + nb * 7, nb * 3 + (size_t)S * 4, cudaMemcpyDeviceToHost, st));
     GSB_CUDA(cudaStreamSynchronize(st));
+    memcpy(filled, h + nb * 7, nb);
+    memcpy(homog, h + nb * 8, nb);
+    memcpy(flag, h + nb * 9, nb);
+    memcpy(detected, h + nb * 10, (size_t)S * 4);
     return rc;
 }
 

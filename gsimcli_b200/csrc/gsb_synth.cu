@@ -26,7 +26,7 @@ __device__ __forceinline__ float synth_value(uint64_t seed, long long r, long lo
     const long long z = node / (dx * dy);
     const long long cx = tri_centered(x, dx), cy = tri_centered(y, dy);
     const long long field = (((cx * cy + (1ll << 18)) * 4800) >> 18) - 4800;
-    const long long mu = 12800 + field + 80 * z;
+    const long long mu = 12800 + field + 80 * (z % 100);   // trend restarts every 100 layers
     const uint64_t key = (seed * 0x94D049BB133111EBull +
                           static_cast<uint64_t>(r) * 0x9E3779B97F4A7C15ull) ^
                          (static_cast<uint64_t>(node) * 0xBF58476D1CE4E5B9ull);

@@ -21,11 +21,12 @@ struct K2Args {
 };
 
 // per-warp scratch region of the counting-sort kernel, in 32-bit words:
-// left halo, NPAD slots + one padding word per IPT slots, overflow bin, right
-// halo; multiples of 4 so the region can be cleared with 16-byte stores
+// left halo, NPAD slots + one padding word per IPT slots, 2 x 32 atom bins and
+// the missing-value bin (aliased by the right halo); multiples of 4 so the
+// region can be cleared with 16-byte stores
 #define K2_CS_LPAD(HALO) (((2 * (HALO)) + 3) & ~3)
 #define K2_CS_REGION_WORDS(IPT, HALO) \
-    ((K2_CS_LPAD(HALO) + (IPT) * 32 + 32 + 2 * (HALO) + 8 + 3) & ~3)
+    ((K2_CS_LPAD(HALO) + (IPT) * 32 + 32 + 72 + 2 * (HALO) + 3) & ~3)
 
 int gsb_launch_k2_csort(gsb_stack* s, const K2Args& args, int ipt, int grid, bool mode,
                         int halo, cudaStream_t st);

@@ -109,6 +109,12 @@ k2_csort_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant_
     // words included, so lane l owns the IPT+1 bins [l*(IPT+1), (l+1)*(IPT+1))
     // and bin b simply lives at word b; word B is the bin of the missing values
     constexpr int B = 32 * (IPT + 1);
+    // the column maximum and minimum are atoms (DSS clamps to [datamin, datamax],
+    // parsers/dss.py:322-325: 65 % of the benchmark columns carry a run of the
+    // maximum, mean 66 values, up to 892 of 1000).  Each gets 32 bins, one per
+    // lane, so that a warp full of equal values still hits 32 different banks
+    // instead of serialising on one address; word INV collects the missing values
+    constexpr int HI0 = B, LO0 = B + 32, INV = B + 64;
     constexpr int W = IPT + 2 * HALO;             // window registers per lane
     constexpr int LPAD = K2_CS_LPAD(HALO);
     constexpr int REG_WORDS = K2_CS_REGION_WORDS(IPT, HALO);
@@ -267,22 +273,26 @@ k2_csort_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant_
                 hi = cs_warp_max(mx);
             }
             // ---- pass 1: histogram; the ATOMS result is the arrival index.
-            // bin = round((x - lo) * scale) + 1 in [1, B-3]; the column extremes
-            // get bins of their own (0 and B-2): DSS clamps to [datamin, datamax]
-            // (parsers/dss.py:322-325), so they are atoms -- often hundreds of
-            // equal values -- that need no sorting; +INF (missing) -> bin B
-            float scale = static_cast<float>(B - 4) / (hi - lo);
+            // regular bin = round((x - lo) * scale) + 1 in [1, B-2]; values equal
+            // to the column maximum / minimum go to this lane's atom bin (an FMA
+            // with a 0/1 factor moves them there); +INF (missing) -> bin INV
+            float scale = static_cast<float>(B - 3) / (hi - lo);
             const bool degenerate = !(scale < INF) || !(scale > 0.f);   // range over/underflow
             if (degenerate) scale = 0.f;
             const float lo_eff = degenerate ? 0.f : lo;
+            const bool allsame = !(lo < hi);     // constant or empty column: nothing to sort
+            const float dhi = static_cast<float>(8388608 + HI0 + lane)
+                            - fmaf(hi - lo_eff, scale, 8388609.0f);
+            const float dlo = allsame ? 0.f : static_cast<float>(8388608 + LO0 + lane)
+                            - fmaf(lo - lo_eff, scale, 8388609.0f);
             uint32_t packed[IPT];
 #pragma unroll
             for (int j = 0; j < IPT; ++j) {
                 const float x = xs[j];
                 float t = fmaf(x - lo_eff, scale, 8388609.0f);
-                t += (x == hi) ? 1.0f : 0.0f;
-                t -= (x == lo) ? 1.0f : 0.0f;
-                const int b = __viaddmin_s32_relu(__float_as_int(t), -0x4B000000, B);
+                t = fmaf((x == hi) ? 1.0f : 0.0f, dhi, t);
+                t = fmaf((x == lo) ? 1.0f : 0.0f, dlo, t);
+                const int b = __viaddmin_s32_relu(__float_as_int(t), -0x4B000000, INV);
                 const uint32_t addr = hbase + static_cast<uint32_t>(b) * 4u;
                 uint32_t old;
                 asm volatile("atom.shared.add.u32 %0, [%1], 1;" : "=r"(old) : "r"(addr) : "memory");
@@ -300,34 +310,34 @@ k2_csort_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant_
             uint32_t bigmask = 0;
             {
                 uint32_t* hp = H + lane * (IPT + 1);
-                uint32_t tot = 0, mc = 0, c_first = 0, c_hi = 0;
+                uint32_t tot = 0, mc = 0;
 #pragma unroll
                 for (int i0 = 0; i0 <= IPT; i0 += 11) {
                     uint32_t cnt[11];
 #pragma unroll
                     for (int u = 0; u < 11; ++u) if (i0 + u <= IPT) cnt[u] = hp[i0 + u];
 #pragma unroll
-                    for (int u = 0; u < 11; ++u) {
-                        const int i = i0 + u;
-                        if (i > IPT) continue;
-                        tot += cnt[u];
-                        // the two atom bins hold equal values only: nothing to sort
-                        if (i == 0) { c_first = cnt[u]; mc = max(mc, lane == 0 ? 0u : cnt[u]); }
-                        else if (i == IPT - 1) { c_hi = cnt[u]; mc = max(mc, lane == 31 ? 0u : cnt[u]); }
-                        else mc = max(mc, cnt[u]);
-                    }
+                    for (int u = 0; u < 11; ++u)
+                        if (i0 + u <= IPT) { tot += cnt[u]; mc = max(mc, cnt[u]); }
                 }
-                uint32_t incl = tot;
+                // exclusive prefixes of the regular bins and of the two atom strips
+                const uint32_t c_hi = H[HI0 + lane], c_lo = H[LO0 + lane];
+                uint32_t incl = tot, incl_hi = c_hi, incl_lo = c_lo;
 #pragma unroll
                 for (int o = 1; o < 32; o <<= 1) {
                     const uint32_t t = __shfl_up_sync(FULL, incl, o);
-                    if (lane >= o) incl += t;
+                    const uint32_t th = __shfl_up_sync(FULL, incl_hi, o);
+                    const uint32_t tl = __shfl_up_sync(FULL, incl_lo, o);
+                    if (lane >= o) { incl += t; incl_hi += th; incl_lo += tl; }
                 }
-                nc = static_cast<int>(__shfl_sync(FULL, incl, 31));
+                n_lo = static_cast<int>(__shfl_sync(FULL, incl_lo, 31));
+                n_hi = static_cast<int>(__shfl_sync(FULL, incl_hi, 31));
+                const int n_reg = static_cast<int>(__shfl_sync(FULL, incl, 31));
+                nc = n_lo + n_reg + n_hi;
                 maxc = static_cast<int>(__reduce_max_sync(FULL, mc));
-                n_lo = static_cast<int>(__shfl_sync(FULL, c_first, 0));
-                n_hi = static_cast<int>(__shfl_sync(FULL, c_hi, 31));
-                uint32_t run = incl - tot;
+                H[LO0 + lane] = incl_lo - c_lo;
+                H[HI0 + lane] = static_cast<uint32_t>(n_lo + n_reg) + incl_hi - c_hi;
+                uint32_t run = static_cast<uint32_t>(n_lo) + incl - tot;
                 if (maxc <= HALO + 1) {
 #pragma unroll
                     for (int i0 = 0; i0 <= IPT; i0 += 11) {
@@ -346,11 +356,8 @@ k2_csort_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant_
                     for (int i = 0; i <= IPT; ++i) {
                         const uint32_t cn = hp[i];
                         hp[i] = run;
-                        const bool atom = (i == 0 && lane == 0) || (i == IPT - 1 && lane == 31);
-                        if (!atom) {
-                            if (cn > HALO + 1) { big_start = run; big_cnt = cn; ++nbig; }
-                            else mc = max(mc, cn);
-                        }
+                        if (cn > HALO + 1) { big_start = run; big_cnt = cn; ++nbig; }
+                        else mc = max(mc, cn);
                         run += cn;
                     }
                     maxc = static_cast<int>(__reduce_max_sync(FULL, mc));
@@ -358,7 +365,7 @@ k2_csort_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant_
                     generic = __any_sync(FULL, nbig > 1u || big_cnt > 128u);
                     bigmask = __ballot_sync(FULL, nbig != 0u);
                 }
-                if (lane == 0) H[B] = static_cast<uint32_t>(nc);   // missing values go last
+                if (lane == 0) H[INV] = static_cast<uint32_t>(nc);   // missing values go last
             }
             __syncwarp();
 
@@ -394,7 +401,6 @@ k2_csort_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant_
                 st_skew = nc < 3 ? fnan : (m2 == 0.f) ? 0.f
                         : __fdividef(fn * sqrtf(fn - 1.f), fn - 2.f) * (m3 * r2 * r2 * r2);
             }
-            const bool allsame = !(lo < hi);     // constant or empty column: nothing to sort
             float w[W];
             if (!allsame) {
                 // ---- pass 2: slot = prefix[bin] + arrival, then scatter
@@ -405,7 +411,7 @@ k2_csort_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant_
                     packed[j] = p + (packed[j] >> 18);
                 }
                 __syncwarp();
-                if (lane < HALO) A[idx(NPAD + lane)] = INF;          // right halo (word B was the overflow bin)
+                if (lane < HALO) A[idx(NPAD + lane)] = INF;          // right halo (aliases the atom strips)
 #pragma unroll
                 for (int j = 0; j < IPT; ++j) A[idx(static_cast<int>(packed[j]))] = xs[j];
                 __syncwarp();
@@ -616,7 +622,7 @@ k2_csort_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant_
             // histogram back to zero for the next column
             {
                 float4* z = reinterpret_cast<float4*>(H);
-                for (int i = lane; i < (B + 4) / 4; i += 32) z[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+                for (int i = lane; i < (INV + 4) / 4; i += 32) z[i] = make_float4(0.f, 0.f, 0.f, 0.f);
             }
             __syncwarp();
         }

@@ -13,7 +13,7 @@ Value model (all in units of 1/16 so that text ``%12.4f``, float64 and float32
 agree exactly -- SURVEY H3, parity mode A):
 
     v16 = clamp(mu16(x, y, z) + noise16(seed, r, node), VMIN16, VMAX16)
-    mu16    = 16*800 + 16*300 * tri(x/dx) * tri(y/dy) + 16*5*z
+    mu16    = 16*800 + 16*300 * tri(x/dx) * tri(y/dy) + 16*5*(z mod 100)
     noise16 = 16*600 * (u1*u2) + 16*100 * u3 - 16*200      (right-skewed)
     value   = v16 / 16,  or ``nodata`` with probability ~1e-3
 
@@ -58,7 +58,9 @@ def values16(seed, r, node, dims):
     cx = _tri_centered(x, dx)
     cy = _tri_centered(y, dy)
     field = (((cx * cy + (1 << 18)) * 4800) >> 18) - 4800
-    mu = 12800 + field + 80 * z
+    # the trend restarts every 100 layers, so that the 100-layer slabs of a
+    # node-sharded multi-GPU run are statistically alike (weak scaling)
+    mu = 12800 + field + 80 * (z % 100)
     with np.errstate(over='ignore'):
         key = (np.uint64(seed) * _M2
                + r.astype(np.uint64) * _GOLD) ^ \

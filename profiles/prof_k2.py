@@ -14,10 +14,11 @@ R = int(sys.argv[1]) if len(sys.argv) > 1 else 1000
 dims = [int(x) for x in (sys.argv[2] if len(sys.argv) > 2 else '200,200,10').split(',')]
 kind = sys.argv[3] if len(sys.argv) > 3 else 'mode'
 reps = int(sys.argv[4]) if len(sys.argv) > 4 else 3
-N = int(np.prod(dims))
+N = int(os.environ.get('GSB_PROF_N', np.prod(dims)))
+NODE0 = int(os.environ.get('GSB_PROF_NODE0', 0))
 QS = [round(0.05 * k, 2) for k in range(1, 20)]
 stack = _capi.Stack(R, N)
-stack.synth_fill(1003, dims, 0, -999.9)
+stack.synth_fill(1003, dims, NODE0, -999.9)
 flags = _capi.MEAN | _capi.SKEW | _capi.VAR | _capi.STD | _capi.COEFVAR
 qs = None
 if kind != 'moments':
