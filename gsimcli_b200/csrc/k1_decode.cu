@@ -145,9 +145,10 @@ __device__ bool parse_float(Ptr p, int len, float* out) {
     } else if (dropped_nonzero) {
         return false;                      // > 19 significant digits: unsupported
     } else {
-        // strip trailing zeros of m so short numbers written with padding stay
-        // on the fast path
-        while (e10 < 0 && (m % 10) == 0) { m /= 10; ++e10; --ndig; }
+        // strip trailing zeros of m only when that is what brings a padded number
+        // back onto the fast path (the quotient m / 10^k is the same rational
+        // either way, and the 64-bit divisions are the slowest thing here)
+        while (ndig > 15 && e10 < 0 && (m % 10) == 0) { m /= 10; ++e10; --ndig; }
         if (ndig <= 15 && e10 >= -22 && e10 <= 22) {
             const double dm = static_cast<double>(static_cast<long long>(m));
             d = (e10 < 0) ? __ddiv_rn(dm, k_pow10[-e10]) : __dmul_rn(dm, k_pow10[e10]);

@@ -38,7 +38,8 @@ __device__ unsigned long long gsb_cs_counters[8];
 namespace {
 
 constexpr unsigned FULL = 0xffffffffu;
-constexpr int CS_WARPS = 16;
+// warps per CTA: as many as the register file allows for the column depth
+template <int IPT> struct CsWarps { static constexpr int v = IPT >= 32 ? 16 : IPT >= 16 ? 24 : 32; };
 
 template <int N> struct CLog2 { static constexpr int v = 1 + CLog2<N / 2>::v; };
 template <> struct CLog2<1> { static constexpr int v = 0; };
@@ -100,8 +101,9 @@ __device__ __forceinline__ uint32_t cs_bits_shift(uint32_t A, int s, int lane) {
 }
 
 template <int IPT, bool MODE, int HALO>
-__global__ void __launch_bounds__(CS_WARPS * 32, 1)
+__global__ void __launch_bounds__(CsWarps<IPT>::v * 32, 1)
 k2_csort_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ K2Args a) {
+    constexpr int CS_WARPS = CsWarps<IPT>::v;
     constexpr int NPAD = IPT * 32;
     constexpr int LOGI = CLog2<IPT>::v;
     constexpr int LOGN = LOGI + 5;
@@ -631,6 +633,7 @@ k2_csort_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant_
 
 template <int IPT, bool MODE, int HALO>
 int cs_launch_one(gsb_stack* s, const K2Args& args, int grid, cudaStream_t st) {
+    constexpr int CS_WARPS = CsWarps<IPT>::v;
     constexpr int NPAD = IPT * 32;
     const size_t smem = static_cast<size_t>(NPAD) * 128
         + static_cast<size_t>(CS_WARPS) * K2_CS_REGION_WORDS(IPT, HALO) * 4 + CS_WARPS * 8 * 4 + 16
