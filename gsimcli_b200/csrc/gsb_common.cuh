@@ -141,16 +141,18 @@ __device__ __forceinline__ void gsb_mbar_expect_tx(uint64_t* bar, uint32_t bytes
                  : "memory");
 }
 __device__ __forceinline__ void gsb_mbar_wait(uint64_t* bar, uint32_t parity) {
+    // try_wait suspends the thread in hardware up to the time hint (ns) before it
+    // reports "not yet": a long hint keeps waiting warps out of the issue slots
     asm volatile(
         "{\n"
         ".reg .pred p;\n"
         "WAIT_%=:\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n"
         "@p bra DONE_%=;\n"
         "bra WAIT_%=;\n"
         "DONE_%=:\n"
         "}\n" ::"r"(gsb_smem_u32(bar)),
-        "r"(parity)
+        "r"(parity), "r"(1000000u)
         : "memory");
 }
 // 2-D TMA tile load, global -> shared::cta, completion on an mbarrier

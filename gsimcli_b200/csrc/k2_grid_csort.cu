@@ -32,7 +32,8 @@
 #include "k2_args.cuh"
 
 // [0] columns, [1] columns with big bins, [2] columns on the generic path,
-// [3] sum of odd-even phases, [4] big bins sorted, [5] values in big bins
+// [3] sum of odd-even phases, [4] big bins sorted, [5] cycles waiting for tiles,
+// [6] cycles of all warps
 __device__ unsigned long long gsb_cs_counters[8];
 
 namespace {
@@ -186,6 +187,7 @@ k2_csort_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant_
     // not the whole block a barrier), and the tile buffer goes back to TMA as
     // soon as its 32 columns sit in registers -- about half a tile time before
     // the last of them is finished.
+    const long long t_begin = clock64();
     for (;;) {
         {
             uint32_t tk = 0;
@@ -195,7 +197,13 @@ k2_csort_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant_
             const int c = static_cast<int>(tk & 31u);
             const long long tile = blockIdx.x + seq * gridDim.x;
             if (tile >= a.ntiles) break;
-            gsb_mbar_wait(full, static_cast<uint32_t>(seq & 1));
+            if (a.lockstep) {
+                const long long t0 = clock64();
+                gsb_mbar_wait(full, static_cast<uint32_t>(seq & 1));
+                if (lane == 0) atomicAdd(&gsb_cs_counters[5], (unsigned long long)(clock64() - t0));
+            } else {
+                gsb_mbar_wait(full, static_cast<uint32_t>(seq & 1));
+            }
             const long long col = tile * 32 + c;
             // ---- column c of the tile -> registers, nodata/NaN/padding -> +INF
             // (128-byte TMA swizzle: 16-byte chunk index ^ (row & 7))
@@ -629,6 +637,8 @@ k2_csort_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant_
             __syncwarp();
         }
     }
+    if (a.lockstep && lane == 0)
+        atomicAdd(&gsb_cs_counters[6], (unsigned long long)(clock64() - t_begin));
 }
 
 template <int IPT, bool MODE, int HALO>

@@ -47,4 +47,5 @@ if os.environ.get('GSB_K2_LOCKSTEP'):
     c = list(buf)
     print('csort counters: columns %d, with big bins %d (%.3f%%), generic %d (%.3f%%), mean phases %.2f, big bins %d' % (
         c[0], c[1], 100.0 * c[1] / max(c[0], 1), c[2], 100.0 * c[2] / max(c[0], 1), c[3] / max(c[0], 1), c[4]))
+    print('tile wait: %.1f%% of warp time (%.0f cycles per column)' % (100.0 * c[5] / max(c[6], 1), c[5] / max(c[0], 1)))
 print('checksum', float(torch.nan_to_num(out).double().sum()))
