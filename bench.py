@@ -225,7 +225,7 @@ def run_gpu(args):
     # K2 runs on its own stream and leaves a few SMs free; the station path
     # (K2c + K3, tiny) runs on a second stream concurrently with it, so its
     # host-side pandas glue overlaps the full-grid kernel
-    stack.set_option('k2_sm_reserve', 4)
+    stack.set_option('k2_sm_reserve', int(os.environ.get('GSB_K2_RESERVE', 4)))
     s_grid = torch.cuda.Stream()
     s_stat = torch.cuda.Stream()
     ev_k0 = torch.cuda.Event(enable_timing=True)
@@ -284,7 +284,10 @@ def run_gpu(args):
 
     # ---- e2e: the float32 stack in pinned host memory, maps back to host
     e2e = None
+    fast = bool(os.environ.get('GSB_BENCH_FAST'))   # developer runs: resident leg only
     try:
+        if fast:
+            raise RuntimeError('skipped (GSB_BENCH_FAST)')
         pitch = stack.pitch
         host = torch.empty((R, pitch), dtype=torch.float32, pin_memory=True)
         dview = torch.empty(0)
@@ -328,7 +331,7 @@ def run_gpu(args):
         achieved = alg_bytes / (k_ms * 1e-3) / 1e9
         cores = len(os.sched_getaffinity(0))
         cpu_nodes = int(os.environ.get('GSB_CPU_NODES', 262144))
-        cpu_val, cpu_wall = cpu_sample(dims, cpu_nodes, 1)
+        cpu_val, cpu_wall = cpu_sample(dims, 4096 if fast else cpu_nodes, 1)
         line = {
             'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world,
             'steps': args.steps, 'warmup': args.warmup,

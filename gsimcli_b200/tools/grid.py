@@ -483,16 +483,24 @@ class GridFiles(object):
             names += ['q{0:g}'.format(q) for q in percentiles]
         if lmode:
             names += ['mode']
-        if len(names) > 3:
+        if len(names) > 3 and self.sharded:
+            # node-sharded stack: reduce only this rank's time layers (the
+            # other layers' nodes live on other GPUs), then gather the small
+            # tables (NCCL over NVLink)
+            from .. import dist
+            per = self.dx * self.dy
+            z0 = self.node0 // per
+            z1 = min(self.dz, -(-(self.node0 + stack.N) // per))
+            part = stack.stats_columns(np.ascontiguousarray(ids[:, z0:z1]), flags,
+                                       p, percentiles, self.nodata, stream)
+            table = np.full((len(nodes), self.dz, part.shape[2]), np.nan)
+            table[:, z0:z1] = part
+            table = dist.allgather_tables(
+                table, [self.dx, self.dy, self.dz],
+                device='cuda:{0}'.format(self.device))
+        elif len(names) > 3:
             table = stack.stats_columns(ids, flags, p, percentiles, self.nodata,
                                         stream)
-            if self.sharded:
-                # node-sharded stack: rows are valid for this rank's time
-                # layers only; gather the small tables (NCCL over NVLink)
-                from .. import dist
-                table = dist.allgather_tables(
-                    table, [self.dx, self.dy, self.dz],
-                    device='cuda:{0}'.format(self.device))
         else:
             table = np.zeros((len(nodes), self.dz, 0))
         z = np.arange(self.zi, self.zi + self.cellz * self.dz)[:self.dz]

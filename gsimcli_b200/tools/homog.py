@@ -263,19 +263,34 @@ def fill_station(pset_file, values, time_min, time_max, time_step=1,
     # `time` and `clim` of the first row (station id), then the fill value
     template = np.concatenate([rows[0, :2], [0.0], rows[0, 3:varcol], [0.0]])
     fillpos = 3 + max(varcol - 3, 0)
-    filled = np.zeros((times.shape[0], ncol))
-    j = 0
-    added = 0
     nrows = have.shape[0]
-    for i, t in enumerate(times):
-        if j < nrows and t == have[j]:
-            filled[i] = rows[j]
-            j += 1
-        else:
-            template[2] = t
-            template[fillpos] = values[i]
-            filled[i] = template[:ncol]
-            added += 1
+    pos = np.searchsorted(times, have)
+    regular = (nrows == 0) or (
+        bool(np.all(np.diff(have) > 0)) and int(pos.max()) < times.shape[0]
+        and bool(np.all(times[pos] == have)))
+    if regular:
+        # the usual case -- observed years strictly increasing and all on the
+        # grid's time axis: the merge walk below matches row j to its year
+        filled = np.empty((times.shape[0], ncol))
+        filled[:] = template[:ncol]
+        filled[:, 2] = times
+        filled[:, fillpos] = np.asarray(values, dtype=np.float64)[:times.shape[0]]
+        if nrows:
+            filled[pos] = rows
+        added = times.shape[0] - nrows
+    else:
+        filled = np.zeros((times.shape[0], ncol))
+        j = 0
+        added = 0
+        for i, t in enumerate(times):
+            if j < nrows and t == have[j]:
+                filled[i] = rows[j]
+                j += 1
+            else:
+                template[2] = t
+                template[fillpos] = values[i]
+                filled[i] = template[:ncol]
+                added += 1
     pset.varnames = names if len(names) == ncol else pset.varnames
     pset.set_array(filled)
     return pset, added

@@ -500,3 +500,32 @@ def test_save_extraction_at_station(tmp_path):
     col[st[:, node] == np.float32(ND)] = np.nan
     assert np.allclose(ps.values['value'].values, col, equal_nan=True)
     g.dump()
+
+
+def test_sharded_stack_reduces_its_own_layers_only():
+    """A node-sharded stack (multi-GPU slab) must give, for its own time
+    layers, exactly the rows of the unsharded table and NaN elsewhere (the
+    other layers come from the other ranks through the table all-gather)."""
+    from gsimcli_b200 import dist
+    dims, first, cells = [12, 10, 9], [0.0, 0.0, 1990], [100.0, 100.0, 1]
+    R = 40
+    st = synth.stack(31, R, dims)
+    full = gr.GridFiles.from_array(st, dims, first, cells, ND)
+    locs = [[250.0, 330.0], [730.0, 610.0], [1010.0, 120.0]]
+    ref = [ps.array() for ps in full.stats_area_many(
+        locs, 1, lmean=True, lmed=True, lperc=True, p=0.9)]
+    full.dump()
+    world = 3
+    for rank in range(world):
+        n0, n1 = dist.slab_range(dims, rank, world)
+        z0, z1 = dist.layer_range(dims, rank, world)
+        part = gr.GridFiles.from_array(st[:, n0:n1], dims, first, cells, ND,
+                                       node_range=(n0, n1))
+        got = [ps.array() for ps in part.stats_area_many(
+            locs, 1, lmean=True, lmed=True, lperc=True, p=0.9)]
+        part.dump()
+        for a, b in zip(got, ref):
+            assert np.array_equal(a[z0:z1], b[z0:z1])
+            assert np.array_equal(a[:, :3], b[:, :3])
+            rest = np.delete(a[:, 3:], np.arange(z0, z1), axis=0)
+            assert np.isnan(rest).all()
