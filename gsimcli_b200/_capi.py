@@ -243,6 +243,50 @@ class Stack(object):
             self.handle, flags, p, q.ctypes.data_as(p_f64), q.size, nodata, n0,
             nn, c_vp(out_ptr), out_pitch, 1, None, stream))
 
+    def stats_grid_from_host(self, host_ptr, host_pitch, flags, p, percentiles,
+                             nodata, out, nslabs=8):
+        """End-to-end K2 from a HOST stack: the ``[R][host_pitch]`` float32
+        matrix at ``host_ptr`` (pinned memory for full PCIe speed) is uploaded
+        in ``nslabs`` node slabs; the reduction of slab k and the download of
+        its maps run while slab k+1 is still on the bus, so the call costs the
+        upload plus one slab of compute.  ``out`` is a pinned float32
+        ``[planes][N]`` torch tensor.  PyTorch supplies the streams/events only."""
+        import torch
+        dev = torch.device('cuda', self.device)
+        q = percentiles if percentiles is not None else []
+        nplanes = lib().gsb_stats_grid_planes(flags, len(q))
+        if getattr(self, '_e2e_maps', None) is None or \
+                self._e2e_maps.shape != (nplanes, self.N):
+            self._e2e_maps = torch.empty((nplanes, self.N), dtype=torch.float32,
+                                         device=dev)
+            self._e2e_up = torch.cuda.Stream(device=dev)
+            self._e2e_run = torch.cuda.Stream(device=dev)
+        up, run, d_maps = self._e2e_up, self._e2e_run, self._e2e_maps
+        cur = torch.cuda.current_stream(dev)
+        up.wait_stream(cur)
+        run.wait_stream(cur)
+        step = -(-self.N // nslabs)
+        step = (step + 31) // 32 * 32             # whole 32-node tiles per slab
+        for a in range(0, self.N, step):
+            b = min(self.N, a + step)
+            check(lib().gsb_stack_upload_f32(
+                self.handle, 0, self.R, a, b - a, c_vp(host_ptr + 4 * a),
+                host_pitch, c_vp(up.cuda_stream)))
+            ev = torch.cuda.Event()
+            ev.record(up)
+            run.wait_event(ev)
+            self.stats_grid_device(flags, p, percentiles, nodata, a, b - a,
+                                   d_maps.data_ptr() + 4 * a, self.N,
+                                   run.cuda_stream)
+            with torch.cuda.stream(run):
+                # one contiguous copy per plane (a strided 2-D tensor copy to
+                # pinned memory goes through a kernel writing over PCIe)
+                for k in range(nplanes):
+                    out[k, a:b].copy_(d_maps[k, a:b], non_blocking=True)
+        cur.wait_stream(run)
+        cur.wait_stream(up)
+        return out
+
     def stats_columns(self, node_ids, flags, p=0.95, percentiles=None,
                       nodata=-999.9, stream=None):
         """K2c: node_ids int64 ``[S][dz][K]`` (local, -1 absent) -> float64
