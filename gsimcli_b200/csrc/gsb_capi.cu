@@ -381,8 +381,9 @@ int gsb_stats_grid(gsb_stack* s, uint32_t flags, double p, const double* q, int 
         d_out = (float*)d;
     }
     if (kernel_ms) GSB_CUDA(cudaEventRecord(s->ev0, st));
-    rc = pl.need_sort ? gsb_launch_k2_sort(s, pl, nodata, n0, nn, d_out, d_pitch, st)
-                      : gsb_launch_k2_moments(s, pl, nodata, n0, nn, d_out, d_pitch, st);
+    rc = !pl.need_sort ? gsb_launch_k2_moments(s, pl, nodata, n0, nn, d_out, d_pitch, st)
+       : s->R <= GSB_MAX_R_GRID ? gsb_launch_k2_sort(s, pl, nodata, n0, nn, d_out, d_pitch, st)
+                                : gsb_launch_k2_deep(s, pl, nodata, n0, nn, d_out, d_pitch, st);
     if (rc) return rc;
     if (kernel_ms) GSB_CUDA(cudaEventRecord(s->ev1, st));
     if (!out_on_device) {

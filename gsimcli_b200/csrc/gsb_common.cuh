@@ -93,6 +93,8 @@ int gsb_launch_k2_sort(gsb_stack* s, const GsbPlanes& pl, float nodata,
 int gsb_launch_k2_moments(gsb_stack* s, const GsbPlanes& pl, float nodata,
                           int64_t n0, int64_t nn, float* d_out,
                           int64_t out_pitch, cudaStream_t st);
+int gsb_launch_k2_deep(gsb_stack* s, const GsbPlanes& pl, float nodata, int64_t n0, int64_t nn,
+                       float* d_out, int64_t out_pitch, cudaStream_t st);
 int gsb_launch_k2_columns(gsb_stack* s, const int64_t* d_node_ids, int S,
                           int dz, int K, const GsbPlanes& pl, float nodata,
                           double* d_table, cudaStream_t st);

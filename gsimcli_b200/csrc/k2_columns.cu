@@ -285,6 +285,52 @@ int gsb_launch_k2_columns(gsb_stack* s, const int64_t* d_node_ids, int S, int dz
     return GSB_OK;
 }
 
+// ---- full-grid statistics through the column kernel -------------------------
+// Columns deeper than the register/shared-memory kernels hold (R > 1024) are
+// rare (the reference recommends "a few hundreds" of realizations,
+// docs/gui.rst:399-404) but must work: every node becomes a K = 1 column of
+// K2c (block-wide sort, in global memory when it does not fit on chip), chunk
+// by chunk, and the float64 table is transposed into the float32 planes.
+namespace {
+__global__ void iota_ids_kernel(long long* ids, long long first, long long n) {
+    const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i < n) ids[i] = first + i;
+}
+__global__ void table_to_planes_kernel(const double* __restrict__ table, int nplanes,
+                                       long long n, float* out, long long out_pitch) {
+    const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    for (int k = 0; k < nplanes; ++k)
+        out[static_cast<long long>(k) * out_pitch + i] = static_cast<float>(table[i * nplanes + k]);
+}
+}  // namespace
+
+int gsb_launch_k2_deep(gsb_stack* s, const GsbPlanes& pl, float nodata, int64_t n0, int64_t nn,
+                       float* d_out, int64_t out_pitch, cudaStream_t st) {
+    // (the column kernel sorts in shared memory up to 51200 values; beyond that
+    // it would need the launcher scratch this function already uses)
+    GSB_REQUIRE(s->R <= 51200, "full-grid order statistics support R <= 51200 (got %lld)",
+                (long long)s->R);
+    const int64_t chunk = 32768;
+    const size_t ids_bytes = static_cast<size_t>(chunk) * 8;
+    void* d = nullptr;
+    int rc = gsb_scratch(s, ids_bytes + static_cast<size_t>(chunk) * pl.n * 8, &d);
+    if (rc) return rc;
+    long long* d_ids = static_cast<long long*>(d);
+    double* d_tab = reinterpret_cast<double*>(static_cast<char*>(d) + ids_bytes);
+    for (int64_t a = 0; a < nn; a += chunk) {
+        const int64_t m = nn - a < chunk ? nn - a : chunk;
+        const int blocks = static_cast<int>((m + 255) / 256);
+        iota_ids_kernel<<<blocks, 256, 0, st>>>(d_ids, n0 + a, m);
+        rc = gsb_launch_k2_columns(s, reinterpret_cast<const int64_t*>(d_ids), static_cast<int>(m),
+                                   1, 1, pl, nodata, d_tab, st);
+        if (rc) return rc;
+        table_to_planes_kernel<<<blocks, 256, 0, st>>>(d_tab, pl.n, m, d_out + a, out_pitch);
+        GSB_CUDA(cudaGetLastError());
+    }
+    return GSB_OK;
+}
+
 int gsb_launch_extract(gsb_stack* s, const int64_t* d_node_ids, int64_t ncols, int K,
                        float* d_values, cudaStream_t st) {
     const long long total = ncols * K * s->R;

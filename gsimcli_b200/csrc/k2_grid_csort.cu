@@ -254,12 +254,10 @@ k2_csort_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant_
                 for (int j = 0; j < IPT; j += 2) {
                     float xm[2];
 #pragma unroll
-                    for (int u = 0; u < 2; ++u) {
-                        const float x = xs[j + u];
-                        xm[u] = x < INF ? x : piv;
-                        mn = fminf(mn, x);
-                        mx = fmaxf(mx, xm[u]);       // piv is an element: a valid stand-in
-                    }
+                    for (int u = 0; u < 2; ++u) xm[u] = xs[j + u] < INF ? xs[j + u] : piv;
+                    // 3-input FMNMX3; piv is an element: a valid stand-in for missing values
+                    asm("min.f32 %0, %0, %1, %2;" : "+f"(mn) : "f"(xs[j]), "f"(xs[j + 1]));
+                    asm("max.f32 %0, %0, %1, %2;" : "+f"(mx) : "f"(xm[0]), "f"(xm[1]));
                     uint64_t d, d2;
                     const uint64_t xx = cs_pack2(xm[0], xm[1]);
                     asm("sub.f32x2 %0, %1, %2;" : "=l"(d) : "l"(xx), "l"(pp));
@@ -591,34 +589,34 @@ k2_csort_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant_
                 }
             }
 
+            // every lane runs the quantile arithmetic (no divergence between the
+            // quantile, moment and mode lanes) and selects its plane at the end
             auto plane_value = [&](int kind, int slot, double q) -> float {
                 const float fnan = __int_as_float(0x7fc00000);
-                if (nc == 0) return fnan;
-                if (kind == GSB_PK_QUANT) {
-                    if (allsame) return vmin;
-                    // np.quantile(method='linear'): h = (n-1) q, NumPy _lerp
-                    const double h = __dmul_rn(dn - 1.0, q);
-                    if (h >= dn - 1.0) return vmax;
-                    if (h < 0.0) return vmin;
-                    const double fl = floor(h);
-                    const int l0 = static_cast<int>(fl);
-                    const double t = h - fl;
-                    const double x0 = static_cast<double>(A[idx(l0)]);
-                    const double x1 = static_cast<double>(A[idx(l0 + 1)]);
-                    const double d = x1 - x0;
-                    const double r = (t >= 0.5) ? __dsub_rn(x1, __dmul_rn(d, 1.0 - t))
-                                                : __dadd_rn(x0, __dmul_rn(d, t));
-                    return static_cast<float>(r);
-                }
-                if (kind == GSB_PK_MODE) return modev;
-                float r = slot == 1 ? st_mean : slot == 2 ? st_var : slot == 3 ? st_sd
+                // np.quantile(method='linear'): h = (n-1) q, NumPy _lerp
+                const double h = __dmul_rn(dn - 1.0, q);
+                const double fl = floor(h);
+                int l0 = static_cast<int>(fl);
+                l0 = max(0, min(l0, nc - 2));
+                const double t = h - fl;
+                float f0 = vmin, f1 = vmin;
+                if (!allsame && nc >= 2) { f0 = A[idx(l0)]; f1 = A[idx(l0 + 1)]; }
+                const double x0 = static_cast<double>(f0), x1 = static_cast<double>(f1);
+                const double d = x1 - x0;
+                const double rq = (t >= 0.5) ? __dsub_rn(x1, __dmul_rn(d, 1.0 - t))
+                                             : __dadd_rn(x0, __dmul_rn(d, t));
+                float r = static_cast<float>(rq);
+                if (h >= dn - 1.0) r = vmax;
+                if (h < 0.0 || allsame) r = vmin;
+                float m = slot == 1 ? st_mean : slot == 2 ? st_var : slot == 3 ? st_sd
                         : slot == 4 ? st_cv : st_skew;
                 if (allsame && slot >= 2) {
-                    if (slot == 4) r = (nc > 1) ? 0.f / st_mean * 100.f : fnan;
-                    else if (slot == 5) r = (nc >= 3) ? 0.f : fnan;
-                    else r = (nc > 1) ? 0.f : fnan;
+                    if (slot == 4) m = (nc > 1) ? 0.f / st_mean * 100.f : fnan;
+                    else if (slot == 5) m = (nc >= 3) ? 0.f : fnan;
+                    else m = (nc > 1) ? 0.f : fnan;
                 }
-                return r;
+                r = kind == GSB_PK_QUANT ? r : kind == GSB_PK_MODE ? modev : m;
+                return nc == 0 ? fnan : r;
             };
             if (col >= a.skip && col < a.nn) {
 #pragma unroll 1

@@ -73,7 +73,8 @@ enum {
 };
 
 #define GSB_MAX_PLANES 64
-#define GSB_MAX_R_GRID 1024 /* largest R of the register-sort grid kernel */
+#define GSB_MAX_R_GRID 1024 /* deepest column of the tile kernels; deeper stacks take the
+                               column kernel node by node (slower, same results) */
 
 int gsb_version(void);
 /* copies the calling thread's last error message into buf (NUL terminated) */

@@ -529,3 +529,11 @@ def test_sharded_stack_reduces_its_own_layers_only():
             assert np.array_equal(a[:, :3], b[:, :3])
             rest = np.delete(a[:, 3:], np.arange(z0, z1), axis=0)
             assert np.isnan(rest).all()
+
+
+def test_grid_stats_deep_columns_beyond_1024():
+    """R > 1024 takes the column kernel node by node (gsb_launch_k2_deep)."""
+    st = synth.stack(77, 1500, [9, 7, 3])
+    st[:, 3] = 812.5
+    st[:, 4] = np.float32(ND)
+    check_grid(st, percentiles=[0.1, 0.5, 0.9])
