@@ -5,7 +5,7 @@ def find(pat, start=0):
     for i in range(start, len(lines)):
         if pat in lines[i]: return i+1
     raise KeyError(pat)
-marks=[('load+sanitize','// ---- column 2w+c of the tile'),('pass0','// ---- pass 0'),('pass1','// ---- pass 1'),('scan','// bins of more than HALO+1'),('momfinal','// ---- moment finals'),('pass2','// ---- pass 2'),('generic','// ---- generic path: bitonic'),('bigbins','// ---- big bins'),('winload','// ---- windows:'),('OET','// max-bin-size phases'),('writeback','float* wq = A'),('mode','// ---- planes'),('planes','auto plane_value'),('zero','// histogram back to zero'),('end','template <int IPT, bool MODE, int HALO>\nint cs_launch_one')]
+marks=[('load+sanitize','// ---- column c of the tile -> registers'),('pass0','// ---- pass 0'),('pass1','// ---- pass 1'),('scan','// bins of more than HALO+1'),('momfinal','// ---- moment finals'),('pass2','// ---- pass 2'),('generic','// ---- generic path: bitonic'),('bigbins','// ---- big bins'),('winload','// ---- windows:'),('OET','// max-bin-size phases'),('writeback','float* wq = A'),('mode','// ---- planes'),('planes','auto plane_value'),('zero','// histogram back to zero'),('end','template <int IPT, bool MODE, int HALO>\nint cs_launch_one')]
 pos=[]
 for name,pat in marks[:-1]:
     pos.append((name,find(pat)))
