@@ -131,6 +131,10 @@ k2_csort_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant_
     uint32_t* ticket = readers + 1;
     double* ptab_q = reinterpret_cast<double*>(full + 2);
     int* ptab_kind = reinterpret_cast<int*>(ptab_q + GSB_MAX_PLANES);
+    // per warp: [0] number of over-full bins of the current column, [1..96] their
+    // (start | count << 16); at most NPAD / (HALO + 2) < 96 of them exist
+    uint32_t* biglist = reinterpret_cast<uint32_t*>(ptab_kind + GSB_MAX_PLANES)
+                      + (threadIdx.x >> 5) * 100;
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -313,9 +317,8 @@ k2_csort_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant_
             // extremes, a dense spot of the distribution) are sorted one by one
             // after the scatter; `maxc` is the largest of the others
             int nc, maxc, n_lo, n_hi;
-            uint32_t big_start = 0, big_cnt = 0, nbig = 0;
+            int nbig = 0;            // over-full bins in this column
             bool generic = false;
-            uint32_t bigmask = 0;
             {
                 uint32_t* hp = H + lane * (IPT + 1);
                 uint32_t tot = 0, mc = 0;
@@ -357,32 +360,36 @@ k2_csort_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant_
                             if (i0 + u <= IPT) { hp[i0 + u] = run; run += cnt[u]; }
                     }
                 } else {
-                    // rare: remember this lane's big bins; `maxc` becomes the
-                    // largest of the small ones
+                    // rare: list the over-full bins; `maxc` becomes the largest
+                    // of the others
+                    if (lane == 0) biglist[0] = 0u;
+                    __syncwarp();
                     mc = 0;
 #pragma unroll 1
                     for (int i = 0; i <= IPT; ++i) {
                         const uint32_t cn = hp[i];
                         hp[i] = run;
-                        if (cn > HALO + 1) { big_start = run; big_cnt = cn; ++nbig; }
-                        else mc = max(mc, cn);
+                        if (cn > HALO + 1) {
+                            const uint32_t k = atomicAdd(biglist, 1u);
+                            if (k < 96u) biglist[1 + k] = run | (cn << 16);
+                        } else {
+                            mc = max(mc, cn);
+                        }
                         run += cn;
                     }
                     maxc = static_cast<int>(__reduce_max_sync(FULL, mc));
-                    // more than one big bin in a lane, or a very big one: generic sort
-                    generic = __any_sync(FULL, nbig > 1u || big_cnt > 128u);
-                    bigmask = __ballot_sync(FULL, nbig != 0u);
+                    __syncwarp();
+                    nbig = static_cast<int>(biglist[0]);
                 }
                 if (lane == 0) H[INV] = static_cast<uint32_t>(nc);   // missing values go last
             }
             __syncwarp();
 
-            if (a.lockstep && lane == 0) {     // GSB_K2_LOCKSTEP doubles as the statistics switch
+            if (a.lockstep && lane == 0) {     // GSB_K2_STATS=1
                 atomicAdd(&gsb_cs_counters[0], 1ull);
-                if (bigmask) atomicAdd(&gsb_cs_counters[1], 1ull);
-                if (generic) atomicAdd(&gsb_cs_counters[2], 1ull);
+                if (nbig) atomicAdd(&gsb_cs_counters[1], 1ull);
                 atomicAdd(&gsb_cs_counters[3], (unsigned long long)maxc);
-                atomicAdd(&gsb_cs_counters[4], (unsigned long long)__popc(bigmask));
+                atomicAdd(&gsb_cs_counters[4], (unsigned long long)nbig);
             }
             // ---- moment finals: warp-uniform, every lane computes them (no
             // shared-memory round trip); the two sums with cancellation in
@@ -424,6 +431,49 @@ k2_csort_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant_
                 for (int j = 0; j < IPT; ++j) A[idx(static_cast<int>(packed[j]))] = xs[j];
                 __syncwarp();
 
+                // ---- over-full bins, the warp on one bin at a time.  A bin whose
+                // values are all equal (heavy ties: quantised data) is already in
+                // order; a mixed one is rank-sorted; a mixed one of more than 128
+                // values (an outlier collapsed the bin map) sends the column to
+                // the generic sort
+#pragma unroll 1
+                for (int e = 0; e < nbig && !generic; ++e) {
+                    const uint32_t ent = biglist[1 + e];
+                    const int s0 = static_cast<int>(ent & 0xffffu);
+                    const int cn = static_cast<int>(ent >> 16);
+                    float bmn = INF, bmx = -INF;
+#pragma unroll 1
+                    for (int i = lane; i < cn; i += 32) {
+                        const float y = A[idx(s0 + i)];
+                        bmn = fminf(bmn, y);
+                        bmx = fmaxf(bmx, y);
+                    }
+                    bmn = cs_warp_min(bmn);
+                    bmx = cs_warp_max(bmx);
+                    if (bmn == bmx) continue;
+                    if (cn > 128) { generic = true; break; }
+                    float mine[4];
+                    int rank[4];
+#pragma unroll
+                    for (int m = 0; m < 4; ++m) {
+                        const int i = lane + 32 * m;
+                        mine[m] = i < cn ? A[idx(s0 + i)] : INF;
+                        rank[m] = 0;
+                    }
+#pragma unroll 1
+                    for (int jx = 0; jx < cn; ++jx) {
+                        const float y = A[idx(s0 + jx)];
+#pragma unroll
+                        for (int m = 0; m < 4; ++m)
+                            rank[m] += (y < mine[m] || (y == mine[m] && jx < lane + 32 * m)) ? 1 : 0;
+                    }
+                    __syncwarp();
+#pragma unroll
+                    for (int m = 0; m < 4; ++m)
+                        if (lane + 32 * m < cn) A[idx(s0 + rank[m])] = mine[m];
+                    __syncwarp();
+                }
+                if (a.lockstep && generic && lane == 0) atomicAdd(&gsb_cs_counters[2], 1ull);
                 if (generic) {
                     // ---- generic path: bitonic sort of the slot array in shared memory
 #pragma unroll 1
@@ -442,33 +492,6 @@ k2_csort_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant_
 #pragma unroll
                     for (int j = 0; j < IPT; ++j) w[HALO + j] = A[lane * (IPT + 1) + j];
                 } else {
-                    // ---- big bins: rank sort, the warp on one bin at a time
-#pragma unroll 1
-                    for (uint32_t bm = bigmask; bm != 0u; bm &= bm - 1u) {
-                        const int src = __ffs(bm) - 1;
-                        const int s0 = static_cast<int>(__shfl_sync(FULL, big_start, src));
-                        const int cn = static_cast<int>(__shfl_sync(FULL, big_cnt, src));
-                        float mine[4];
-                        int rank[4];
-#pragma unroll
-                        for (int m = 0; m < 4; ++m) {
-                            const int i = lane + 32 * m;
-                            mine[m] = i < cn ? A[idx(s0 + i)] : INF;
-                            rank[m] = 0;
-                        }
-#pragma unroll 1
-                        for (int jx = 0; jx < cn; ++jx) {
-                            const float y = A[idx(s0 + jx)];
-#pragma unroll
-                            for (int m = 0; m < 4; ++m)
-                                rank[m] += (y < mine[m] || (y == mine[m] && jx < lane + 32 * m)) ? 1 : 0;
-                        }
-                        __syncwarp();
-#pragma unroll
-                        for (int m = 0; m < 4; ++m)
-                            if (lane + 32 * m < cn) A[idx(s0 + rank[m])] = mine[m];
-                        __syncwarp();
-                    }
                     // ---- windows: [l*IPT - HALO, (l+1)*IPT + HALO) -> registers
                     const float* wp = A + lane * (IPT + 1);
 #pragma unroll
@@ -520,8 +543,8 @@ k2_csort_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant_
                     if (mloc <= 0) M = 0;
                     else if (mloc < IPT) M &= (1u << mloc) - 1u;
                     int pe = 0, best = 1;
-                    if (generic) {
-                        // generic path: runs of any length, binary lifting
+                    if (generic || nbig) {
+                        // runs of any length: binary lifting
                         uint32_t P[LOGN + 1];
                         P[0] = M;
                         int top = __any_sync(FULL, M != 0) ? 0 : -1;
@@ -645,7 +668,7 @@ int cs_launch_one(gsb_stack* s, const K2Args& args, int grid, cudaStream_t st) {
     constexpr int NPAD = IPT * 32;
     const size_t smem = static_cast<size_t>(NPAD) * 128
         + static_cast<size_t>(CS_WARPS) * K2_CS_REGION_WORDS(IPT, HALO) * 4 + CS_WARPS * 8 * 4 + 16
-        + GSB_MAX_PLANES * 12;
+        + GSB_MAX_PLANES * 12 + CS_WARPS * 100 * 4;
     auto kern = k2_csort_kernel<IPT, MODE, HALO>;
     GSB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   static_cast<int>(smem)));

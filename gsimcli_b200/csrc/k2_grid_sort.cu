@@ -593,8 +593,12 @@ int gsb_launch_k2_sort(gsb_stack* s, const GsbPlanes& pl, float nodata, int64_t 
     args.nchunks = static_cast<int>((s->R + 31) / 32);
     args.nplanes = pl.n;
     args.nodata = nodata;
+    // GSB_K2_LOCKSTEP: block barriers inside the bitonic kernel (experiment);
+    // GSB_K2_STATS: diagnostic counters of the counting-sort kernel
+    // (gsb_debug_cs_counters).  Both travel in the same field.
     const char* ls = getenv("GSB_K2_LOCKSTEP");
-    args.lockstep = ls ? atoi(ls) : 0;
+    const char* sts = getenv("GSB_K2_STATS");
+    args.lockstep = (ls ? atoi(ls) : 0) | (sts ? atoi(sts) : 0);
     const char* sk = getenv("GSB_K2_SKEW");
     args.skew = sk ? atoi(sk) : 1;
     const int64_t head = n0 & 3;

@@ -207,7 +207,7 @@ int gsb_detect(const double* clim, const double* mean, const double* lperc,
 
 /* ---- diagnostics ----------------------------------------------------------
  * Counters of the counting-sort K2 kernel, accumulated only while the
- * environment variable GSB_K2_LOCKSTEP is non-zero: out[0] columns reduced,
+ * environment variable GSB_K2_STATS is non-zero: out[0] columns reduced,
  * [1] columns that held an over-full bin, [2] columns that took the generic
  * shared-memory sort, [3] sum of odd-even phases, [4] over-full bins sorted, [5] SM cycles warps
  * spent waiting for a tile, [6] SM cycles of all warps.

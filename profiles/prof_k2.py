@@ -40,7 +40,7 @@ for i in range(reps):
     gbs = (4.0 * R * N + 4.0 * npl * N) / ms / 1e6
     print('%s R=%d N=%d planes=%d: %.3f ms  %.1f GB/s  %.3e node-real/s' % (
         kind, R, N, npl, ms, gbs, R * N / ms * 1e3))
-if os.environ.get('GSB_K2_LOCKSTEP'):
+if os.environ.get('GSB_K2_STATS'):
     import ctypes
     buf = (ctypes.c_ulonglong * 8)()
     _capi.lib().gsb_debug_cs_counters(buf, 1)

@@ -537,3 +537,25 @@ def test_grid_stats_deep_columns_beyond_1024():
     st[:, 3] = 812.5
     st[:, 4] = np.float32(ND)
     check_grid(st, percentiles=[0.1, 0.5, 0.9])
+
+
+def test_pipelined_host_path_equals_resident_path():
+    """Stack.stats_grid_from_host (slab-pipelined upload + K2 + download, the
+    bench's e2e leg) must give the maps of upload + stats_grid bit for bit."""
+    import torch
+    R, dims = 200, [31, 17, 6]
+    st = synth.stack(9, R, dims)
+    N = st.shape[1]
+    stack = _capi.Stack(R, N)
+    stack.upload(st)
+    flags = ALLF | _capi.MODE
+    ref = stack.stats_grid(flags, 0.95, QS, ND)
+    host = torch.zeros((R, stack.pitch), dtype=torch.float32).pin_memory()
+    host[:, :N] = torch.from_numpy(st)
+    out = torch.empty((ref.shape[0], N), dtype=torch.float32).pin_memory()
+    stack.upload(np.zeros_like(st))            # make sure the data really comes from `host`
+    stack.stats_grid_from_host(host.data_ptr(), stack.pitch, flags, 0.95, QS, ND,
+                               out, nslabs=5)
+    torch.cuda.synchronize()
+    stack.close()
+    assert np.array_equal(out.numpy().view(np.int32), ref.view(np.int32))
