@@ -240,16 +240,24 @@ k2_csort_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant_
             }
 
             // ---- pass 0: pivot, shifted moments (packed f32x2), min / max
-            // pivot of the shifted sums: the first valid value among the first 32
-            // realizations.  An actual element, so a constant column gives d == 0
-            // exactly and the max below may use it as the stand-in for missing
-            // values; within a few sigma of the mean, which is all the float32
-            // shifted sums need
+            // pivot of the shifted sums: an actual element (a constant column gives
+            // d == 0 exactly, and the max below may use it as the stand-in for
+            // missing values) within a few sigma of the mean, which is all the
+            // float32 shifted sums need
             float piv, S1, S2, S3, lo, hi;
             {
+                // median of the first three valid values among the first 32
+                // realizations: one outlier among them cannot become the pivot
                 const uint32_t okm = __ballot_sync(FULL, xs[0] < INF);
                 const bool have_piv = okm != 0u;
-                const float cand = __shfl_sync(FULL, xs[0], have_piv ? __ffs(okm) - 1 : 0);
+                const uint32_t m1 = okm & (okm - 1u), m2 = m1 & (m1 - 1u);
+                const int l0 = have_piv ? __ffs(okm) - 1 : 0;
+                const int l1 = m1 ? __ffs(m1) - 1 : l0;
+                const int l2 = m2 ? __ffs(m2) - 1 : l0;
+                const float c0 = __shfl_sync(FULL, xs[0], l0);
+                const float c1 = __shfl_sync(FULL, xs[0], l1);
+                const float c2 = __shfl_sync(FULL, xs[0], l2);
+                const float cand = fmaxf(fminf(c0, c1), fminf(fmaxf(c0, c1), c2));
                 piv = have_piv ? cand : 0.f;
                 float mn = INF, mx = have_piv ? cand : -INF;
                 uint64_t s1 = 0, s2 = 0, s3 = 0;

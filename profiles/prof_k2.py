@@ -21,7 +21,9 @@ stack = _capi.Stack(R, N)
 stack.synth_fill(1003, dims, NODE0, -999.9)
 flags = _capi.MEAN | _capi.SKEW | _capi.VAR | _capi.STD | _capi.COEFVAR
 qs = None
-if kind != 'moments':
+if kind == 'refapi':          # the reference's stats(): moments + median + percentile pair
+    flags |= _capi.MEDIAN | _capi.PERC
+elif kind != 'moments':
     flags |= _capi.MEDIAN
     qs = QS
 if kind == 'mode':

@@ -559,3 +559,28 @@ def test_pipelined_host_path_equals_resident_path():
     torch.cuda.synchronize()
     stack.close()
     assert np.array_equal(out.numpy().view(np.int32), ref.view(np.int32))
+
+
+@pytest.mark.parametrize('R', [129, 200, 333, 500, 1000, 1024])
+def test_grid_stats_reference_api_call(R):
+    """The reference's own stats() call: moments, median, percentile pair, no
+    percentile list, no mode (the MODE = false instantiation of the kernels)."""
+    rng = np.random.default_rng(R)
+    dims = [16, 11, 4]
+    st = synth.stack(3000 + R, R, dims)
+    st[:, 3] = 812.5                                  # constant
+    st[:, 4] = np.float32(ND)                         # empty
+    st[:, 5] = np.float32(ND)
+    st[R // 2, 5] = 640.25                            # n == 1
+    st[:, 6] = np.float32(ND)
+    st[0, 6], st[R - 1, 6] = 7.5, 8.5                 # n == 2
+    st[:, 8] = np.where(np.arange(R) % 2 == 0, 500.0, 600.0)          # two atoms
+    st[:, 9] = rng.integers(0, 5, size=R) * 0.5                        # heavy ties
+    st[:, 10] = np.where(rng.uniform(size=R) < 0.7, 0.0,
+                         np.round(rng.gamma(2.0, 20.0, size=R) * 16) / 16)   # zero-inflated
+    st[0, 11] = 3.0e8                                 # outlier collapses the bin map
+    st[:, 12] = np.round(rng.normal(0.0, 1.0, size=R) * 4) / 4 + np.where(
+        rng.uniform(size=R) < 0.5, -1.0e6, 1.0e6)     # two far clusters
+    for p in (0.95, 0.5, 1.0, 0.1):
+        check_grid(st, p=p, percentiles=None, mode=False)
+    check_grid(st, p=0.9, percentiles=[0.0], mode=False)      # > 3 quantile planes: full path
