@@ -584,3 +584,14 @@ def test_grid_stats_reference_api_call(R):
     for p in (0.95, 0.5, 1.0, 0.1):
         check_grid(st, p=p, percentiles=None, mode=False)
     check_grid(st, p=0.9, percentiles=[0.0], mode=False)      # > 3 quantile planes: full path
+
+
+def test_sort_kernels_agree_on_random_stacks():
+    """Short run of profiles/stress_k2.py: counting-sort and bitonic kernels
+    must give bit-identical order statistics and modes on random stacks of
+    smooth, tied, clamped, clustered, offset, outlier and heavy-tailed columns."""
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, os.path.join(root, 'profiles', 'stress_k2.py'), '5'],
+                       capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
