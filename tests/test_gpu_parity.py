@@ -7,6 +7,7 @@ counts and node indexing.  <= 1e-5 relative (absolute floor for skewness near
 agree with the oracle to summation-order noise (1e-12 relative).
 """
 import os
+import sys
 
 import numpy as np
 import pandas as pd
