@@ -14,7 +14,8 @@ exchange is the all-gather of the per-station tables).
 
 Keys of the JSON line: see the task contract.  ``value`` = node-realizations/s
 with the stack resident in HBM; ``e2e`` = the same through the public API with
-the float32 stack in pinned HOST memory (H2D of the stack + D2H of every map
+the float32 stack in pinned HOST memory (H2D of the stack in node slabs, each
+slab's reduction and the D2H of its maps overlapped with the next upload -- all
 inside the timed region); ``roofline`` for the dominant kernel (K2) against
 the measured HBM peak; ``cpu_baseline`` = the NumPy oracle on a bounded sample
 on the host cores.
@@ -353,6 +354,7 @@ def run_gpu(args):
             'gpu_launches': 3 * args.steps,
             'roofline': {'bound': 'hbm', 'achieved': achieved, 'peak': peak,
                          'unit': 'GB/s', 'frac': achieved / peak,
+                         'frac_of_nominal_8TBs': achieved / 8000.0,
                          'traffic': measured_traffic(R, nn), 'kernel': 'k2_csort_kernel',
                          'kernel_ms': k_ms, 'algorithmic_bytes': alg_bytes,
                          'peak_source': peak_src},
