@@ -165,6 +165,70 @@ __device__ bool parse_float(Ptr p, int len, float* out) {
 }
 
 // ------------------------------------------------------------ fixed width
+// Fast path for the record DSS writes ('%W.Pf' + EOL, W <= 16 bytes): blanks, an
+// optional sign, digits with exactly one '.', then only end-of-line blanks.
+// The 16 bytes are classified in registers (SWAR digit / blank masks -> one
+// 16-bit mask each), the structure is validated on the masks, and the digits
+// are accumulated by one short Horner loop; the conversion is the same
+// correctly-rounded divide as in parse_float, so the result is bit-identical.
+// Anything else (exponents, inf/nan, no '.', > 15 digits, odd characters)
+// returns false and takes parse_float.
+__device__ __forceinline__ unsigned k1_movemask(unsigned hibits) {
+    // bit i of the result = bit 7 of byte i
+    return (((hibits >> 7) & 0x01010101u) * 0x01020408u) >> 24;
+}
+
+__device__ __forceinline__ bool parse_fixed_fast(const unsigned char* p, int W, float* out) {
+    const unsigned addr = static_cast<unsigned>(__cvta_generic_to_shared(p));
+    const unsigned sh = (addr & 3u) * 8u;
+    const unsigned* wp = reinterpret_cast<const unsigned*>(p - (addr & 3u));
+    unsigned w[5];
+#pragma unroll
+    for (int k = 0; k < 5; ++k) w[k] = wp[k];
+    unsigned nd16 = 0, sp16 = 0;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const unsigned u = __funnelshift_r(w[k], w[k + 1], sh);
+        const unsigned t = u ^ 0x30303030u;                       // digits -> 0..9
+        const unsigned nd = (((t & 0x7f7f7f7fu) + 0x76767676u) | t) & 0x80808080u;
+        const unsigned z = u ^ 0x20202020u;                       // ' ' -> 0
+        const unsigned nz = (((z & 0x7f7f7f7fu) + 0x7f7f7f7fu) | z) & 0x80808080u;
+        nd16 |= k1_movemask(nd) << (4 * k);
+        sp16 |= (k1_movemask(nz) ^ 0xfu) << (4 * k);
+    }
+    const unsigned inw = (1u << W) - 1u;
+    const unsigned dg = ~nd16 & inw;
+    if (dg == 0u) return false;
+    const int f = __ffs(dg) - 1;
+    const int l = 31 - __clz(dg);
+    const unsigned inner = nd16 & ((2u << l) - 1u) & ~((1u << f) - 1u);
+    if (__popc(inner) != 1) return false;
+    const int pdot = __ffs(inner) - 1;
+    if (p[pdot] != '.') return false;
+    for (int i = l + 1; i < W; ++i) {                   // end-of-line blanks only
+        const unsigned c = p[i];
+        if (!(c == ' ' || (c >= 9 && c <= 13))) return false;
+    }
+    int lead = f;                                       // bytes before the sign / first digit
+    bool negv = false;
+    if (f > 0) {
+        const unsigned c = p[f - 1];
+        if (c == '-' || c == '+') { negv = (c == '-'); lead = f - 1; }
+    }
+    const unsigned leadmask = (1u << lead) - 1u;
+    if ((sp16 & leadmask) != leadmask) return false;   // something else than ' ' in front
+    if (l - f > 15) return false;                       // > 15 digits: not the fast path
+    unsigned long long m = 0;
+    for (int i = f; i <= l; ++i)
+        if (i != pdot) m = m * 10ull + (p[i] - '0');
+    const int nfrac = l - pdot;
+    double d = static_cast<double>(static_cast<long long>(m));
+    if (m != 0ull && nfrac > 0) d = __ddiv_rn(d, k_pow10[nfrac]);
+    if (negv) d = -d;
+    *out = __double2float_rn(d);
+    return true;
+}
+
 __global__ void __launch_bounds__(K1_THREADS)
 k1_decode_fixed(const char* __restrict__ text, long long nbytes, int W, long long nlines,
                 float* __restrict__ out, long long* bad_line) {
@@ -201,7 +265,8 @@ k1_decode_fixed(const char* __restrict__ text, long long nbytes, int W, long lon
         if (li < nl) {
             const unsigned char* p = sm + mis + static_cast<long long>(li) * W;
             float val;
-            bool ok = (p[W - 1] == '\n') && parse_float(p, W, &val);
+            bool ok = (p[W - 1] == '\n') &&
+                      ((W <= 16 && parse_fixed_fast(p, W, &val)) || parse_float(p, W, &val));
             if (ok) out[line0 + li] = val;
             else atomicMin(reinterpret_cast<unsigned long long*>(bad_line),
                            static_cast<unsigned long long>(line0 + li));
