@@ -218,12 +218,21 @@ __device__ __forceinline__ bool parse_fixed_fast(const unsigned char* p, int W, 
     const unsigned leadmask = (1u << lead) - 1u;
     if ((sp16 & leadmask) != leadmask) return false;   // something else than ' ' in front
     if (l - f > 15) return false;                       // > 15 digits: not the fast path
-    unsigned long long m = 0;
-    for (int i = f; i <= l; ++i)
-        if (i != pdot) m = m * 10ull + (p[i] - '0');
     const int nfrac = l - pdot;
-    double d = static_cast<double>(static_cast<long long>(m));
-    if (m != 0ull && nfrac > 0) d = __ddiv_rn(d, k_pow10[nfrac]);
+    double d;
+    if (l - f <= 9) {                                   // <= 9 digits: 32-bit Horner
+        unsigned m = 0;
+        for (int i = f; i < pdot; ++i) m = m * 10u + (p[i] - '0');
+        for (int i = pdot + 1; i <= l; ++i) m = m * 10u + (p[i] - '0');
+        d = static_cast<double>(m);
+        if (m != 0u) d = __ddiv_rn(d, k_pow10[nfrac]);
+    } else {
+        unsigned long long m = 0;
+        for (int i = f; i < pdot; ++i) m = m * 10ull + (p[i] - '0');
+        for (int i = pdot + 1; i <= l; ++i) m = m * 10ull + (p[i] - '0');
+        d = static_cast<double>(static_cast<long long>(m));
+        if (m != 0ull) d = __ddiv_rn(d, k_pow10[nfrac]);
+    }
     if (negv) d = -d;
     *out = __double2float_rn(d);
     return true;
