@@ -40,7 +40,7 @@ namespace {
 
 constexpr unsigned FULL = 0xffffffffu;
 // warps per CTA: as many as the register file allows for the column depth
-template <int IPT> struct CsWarps { static constexpr int v = IPT >= 32 ? 16 : IPT >= 16 ? 24 : 32; };
+template <int IPT> struct CsWarps { static constexpr int v = IPT >= 32 ? 16 : IPT >= 16 ? 24 : 32; };   // 128 / 80 / 64 registers
 
 template <int N> struct CLog2 { static constexpr int v = 1 + CLog2<N / 2>::v; };
 template <> struct CLog2<1> { static constexpr int v = 0; };
@@ -688,6 +688,7 @@ int cs_launch_one(gsb_stack* s, const K2Args& args, int grid, cudaStream_t st) {
 template <bool MODE, int HALO>
 int cs_launch_ipt(gsb_stack* s, const K2Args& args, int ipt, int grid, cudaStream_t st) {
     switch (ipt) {
+    case 4: return cs_launch_one<4, MODE, HALO>(s, args, grid, st);
     case 8: return cs_launch_one<8, MODE, HALO>(s, args, grid, st);
     case 16: return cs_launch_one<16, MODE, HALO>(s, args, grid, st);
     case 32: return cs_launch_one<32, MODE, HALO>(s, args, grid, st);
