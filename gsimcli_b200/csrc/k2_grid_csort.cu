@@ -1,5 +1,5 @@
 // k2_grid_csort.cu -- K2, counting-sort variant: realization-axis reduction
-// with exact order statistics for 64 < R <= 1024.
+// with exact order statistics for 32 < R <= 1024.
 //
 // Same contract as k2_grid_sort.cu (GridFiles.stats cell loop,
 // GSIMCLI/tools/grid.py:662-701): per grid node, R realization values ->
@@ -688,6 +688,7 @@ int cs_launch_one(gsb_stack* s, const K2Args& args, int grid, cudaStream_t st) {
 template <bool MODE, int HALO>
 int cs_launch_ipt(gsb_stack* s, const K2Args& args, int ipt, int grid, cudaStream_t st) {
     switch (ipt) {
+    case 2: return cs_launch_one<2, MODE, HALO>(s, args, grid, st);
     case 4: return cs_launch_one<4, MODE, HALO>(s, args, grid, st);
     case 8: return cs_launch_one<8, MODE, HALO>(s, args, grid, st);
     case 16: return cs_launch_one<16, MODE, HALO>(s, args, grid, st);

@@ -614,11 +614,11 @@ int gsb_launch_k2_sort(gsb_stack* s, const GsbPlanes& pl, float nodata, int64_t 
     const int ctas = s->sm_count - s->k2_sm_reserve;
     const int grid = static_cast<int>(args.ntiles < ctas ? args.ntiles : ctas);
     if (grid <= 0) return GSB_OK;
-    // counting-sort kernel for the deep columns (default for R > 64); the
+    // counting-sort kernel for the deep columns (default for R > 32); the
     // register bitonic sort below stays the kernel for shallow ones
     const char* alg = getenv("GSB_K2_ALGO");
-    const bool want_cs = alg ? (strcmp(alg, "csort") == 0) : (ipt >= 4);
-    if (want_cs && ipt >= 4) {
+    const bool want_cs = alg ? (strcmp(alg, "csort") == 0) : (ipt >= 2);
+    if (want_cs && ipt >= 2) {
         const char* hl = getenv("GSB_K2_HALO");
         return gsb_launch_k2_csort(s, args, ipt, grid, pl.need_mode != 0, hl ? atoi(hl) : 10, st);
     }
