@@ -13,7 +13,7 @@ rng = np.random.default_rng(2026)
 flags = _capi.MEAN | _capi.MEDIAN | _capi.SKEW | _capi.VAR | _capi.STD | _capi.COEFVAR | _capi.PERC | _capi.MODE
 bad = 0
 for it in range(rounds):
-    R = int(rng.integers(129, 1025))
+    R = int(rng.integers(33, 1025))
     N = int(rng.integers(3000, 9000))
     kind = rng.integers(0, 8, size=N)
     base = rng.normal(0.0, 1.0, size=(R, N))
