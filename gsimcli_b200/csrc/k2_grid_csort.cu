@@ -7,26 +7,33 @@
 //
 // A comparison sort of a 1024-value column costs ~110 instructions per value
 // (k2_grid_sort.cu: 11 % of the HBM roofline).  This kernel sorts by
-// DISTRIBUTION instead:
-//   HBM stack [R][pitch] f32 --TMA 32-node boxes, 128B swizzle--> one 128 KB
-//   tile per CTA --LDS.64, conflict free--> registers (warp w owns nodes
-//   2w, 2w+1; lane l holds rows 32 j + l), tile buffer refilled by TMA at once.
-//   pass 0  registers: nodata/NaN -> +INF, shifted moments, column min/max
-//   pass 1  bin = linear map of [min, max] onto B = NPAD bins; one shared-memory
-//           ATOMS.ADD per value returns its arrival index inside the bin
-//   scan    per-bin exclusive prefix (lane l owns bins l*IPT..; stride IPT+1
-//           padding keeps every LDS/STS bank-conflict free)
+// DISTRIBUTION instead.  One persistent CTA per SM (16 / 24 / 32 warps for
+// R <= 1024 / 512 / 256):
+//   HBM stack [R][pitch] f32 --TMA 32-node boxes, 128B swizzle--> one tile per
+//   CTA; its 32 columns are handed to the warps by a ticket counter; a warp
+//   copies its column to registers (lane l holds rows 32 j + l) and the warp
+//   that takes the last column re-arms the mbarrier and issues the TMA of the
+//   CTA's next tile.  Per column, in registers + a per-warp scratch region:
+//   pass 0  nodata/NaN -> +INF, shifted moments (packed f32x2), min / max
+//   pass 1  bin = linear map of [min, max] onto B = 32 (IPT+1) bins; values
+//           equal to min / max go to per-lane atom bins (DSS clamps, so the
+//           extremes are often runs of hundreds of equal values); one
+//           shared-memory ATOMS.ADD per value returns its arrival index
+//   scan    per-bin exclusive prefix (lane l owns bins l (IPT+1)...: stride
+//           IPT+1 keeps every LDS/STS bank-conflict free)
 //   pass 2  value -> slot prefix[bin] + arrival (the slot array aliases the
 //           histogram: prefixes are read into registers first)
+//   big     bins of more than HALO+1 values: skipped when all equal (heavy
+//           ties), rank-sorted by the warp otherwise
 //   windows lane l re-reads slots [l*IPT - HALO, (l+1)*IPT + HALO) into
 //           registers and runs max-bin-size odd-even transposition phases:
 //           bins are value-ordered, so exchanges never cross a bin boundary
 //           and every bin <= HALO+1 values that touches the lane's own slots
 //           is sorted completely inside the window
-//   columns whose largest bin exceeds HALO+1 (heavy ties, outliers) take a
-//   generic shared-memory bitonic sort instead -- always exact.
+//   a column whose bin map collapsed (an outlier: one mixed bin of > 128
+//   values) takes a generic shared-memory bitonic sort instead -- always exact.
 //   finish  quantile lerp in float64 (NumPy _lerp), mode from the equal-
-//           neighbour bitmap, moments in float64; lane = output plane.
+//           neighbour bitmap, moments in float32/64; lane = output plane.
 // HBM traffic: the stack is read exactly once (4 B per node-realization).
 #include "gsb_common.cuh"
 #include "k2_args.cuh"
@@ -77,14 +84,10 @@ __device__ __forceinline__ uint64_t cs_pack2(float a, float b) {
     return r;
 }
 __device__ __forceinline__ float cs_lo2(uint64_t v) {
-    float a, b;
-    asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v));
-    return a;
+    return __uint_as_float(static_cast<uint32_t>(v));
 }
 __device__ __forceinline__ float cs_hi2(uint64_t v) {
-    float a, b;
-    asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v));
-    return b;
+    return __uint_as_float(static_cast<uint32_t>(v >> 32));
 }
 
 // B(p) = A(p - s) over the NPAD-bit string distributed IPT bits per lane
@@ -125,8 +128,7 @@ k2_csort_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant_
     constexpr int BOX_ROWS = NPAD < 256 ? NPAD : 256;  // must match make_tmap()
     extern __shared__ __align__(1024) unsigned char smem[];
     uint32_t* scratch_all = reinterpret_cast<uint32_t*>(smem + TILE_BYTES);
-    float* cstat_all = reinterpret_cast<float*>(scratch_all + CS_WARPS * REG_WORDS);
-    uint64_t* full = reinterpret_cast<uint64_t*>(cstat_all + CS_WARPS * 8);
+    uint64_t* full = reinterpret_cast<uint64_t*>(scratch_all + CS_WARPS * REG_WORDS);
     uint32_t* readers = reinterpret_cast<uint32_t*>(full + 1);
     uint32_t* ticket = readers + 1;
     double* ptab_q = reinterpret_cast<double*>(full + 2);
@@ -675,7 +677,7 @@ int cs_launch_one(gsb_stack* s, const K2Args& args, int grid, cudaStream_t st) {
     constexpr int CS_WARPS = CsWarps<IPT>::v;
     constexpr int NPAD = IPT * 32;
     const size_t smem = static_cast<size_t>(NPAD) * 128
-        + static_cast<size_t>(CS_WARPS) * K2_CS_REGION_WORDS(IPT, HALO) * 4 + CS_WARPS * 8 * 4 + 16
+        + static_cast<size_t>(CS_WARPS) * K2_CS_REGION_WORDS(IPT, HALO) * 4 + 16
         + GSB_MAX_PLANES * 12 + CS_WARPS * 100 * 4;
     auto kern = k2_csort_kernel<IPT, MODE, HALO>;
     GSB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
