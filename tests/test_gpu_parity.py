@@ -596,3 +596,17 @@ def test_sort_kernels_agree_on_random_stacks():
     r = subprocess.run([sys.executable, os.path.join(root, 'profiles', 'stress_k2.py'), '5'],
                        capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+
+
+def test_grid_stats_more_than_32_planes():
+    """48 output planes (40 percentiles + moments + pair + mode): two rounds of
+    the lane = plane output loop."""
+    st = synth.stack(12, 300, [10, 9, 4])
+    qs = [round(0.025 * k, 3) for k in range(40)]
+    check_grid(st, percentiles=qs)
+    with pytest.raises(ValueError):
+        stack = _capi.Stack(8, 64)
+        try:
+            stack.stats_grid(ALLF | _capi.MODE, 0.95, [0.5] * 60, ND)    # 69 planes > 64
+        finally:
+            stack.close()
