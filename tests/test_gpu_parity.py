@@ -610,3 +610,20 @@ def test_grid_stats_more_than_32_planes():
             stack.stats_grid(ALLF | _capi.MODE, 0.95, [0.5] * 60, ND)    # 69 planes > 64
         finally:
             stack.close()
+
+
+def test_moments_only_kernel_with_outlier_in_first_rows():
+    """The shifted float32 sums must not take an outlier as their pivot."""
+    flags = _capi.MEAN | _capi.SKEW | _capi.VAR | _capi.STD | _capi.COEFVAR
+    st = synth.stack(78, 400, [10, 8, 3])
+    st[0, :40] = 3.0e8                 # the first realization of 40 nodes is an outlier
+    st[1, 40:80] = -2.0e8
+    stack = _capi.Stack(*st.shape)
+    stack.upload(st)
+    out = stack.stats_grid(flags, 0.95, None, ND)
+    stack.close()
+    ref = O.grid_stats(st, ND, flags)
+    close(out[0], ref['meanmap'])
+    close(out[2], ref['varmap'])
+    close(out[3], ref['stdmap'])
+    close(out[1], ref['skewmap'], rtol=1e-4, atol=2e-4)
