@@ -238,6 +238,80 @@ def detect_many(grids, obs_list, rad=0, method='mean', prob=0.95,
     return out
 
 
+def detect_sweep(grids, obs_list, probs, rad=0, method='mean', skewness=None,
+                 flag=True, header=True, optional_stats=None, stream=None):
+    """Extension: ``detect_many`` for several detection probabilities at once
+    (the per-network probability sweep of batch homogenisation).  The station
+    columns are reduced ONCE -- a sweep over ``prob`` only changes which sorted
+    ranks are read -- so one K2c launch serves every probability and only the
+    tiny K3 step is repeated.  Returns ``{prob: [detect-style tuples]}``; each
+    entry equals ``detect_many(..., prob=prob)``."""
+    if method == 'percentile':
+        raise ValueError('detect_sweep: the percentile method has its own '
+                         'interval; call detect_many per probability')
+    probs = [float(p) for p in probs]
+    if not probs:
+        return {}
+    sel = _select_stats(method, skewness, optional_stats)
+    prepared = [_prepare_obs(o, grids, header) for o in obs_list]
+    locs = [p[1] for p in prepared]
+    extra = []
+    for p in probs[1:]:
+        extra += [(1 - p) / 2, 1 - (1 - p) / 2]            # grid.py:700-701
+    psets = grids.stats_area_many(locs, rad, p=probs[0], stream=stream,
+                                  percentiles=extra or None, **sel)
+    S, dz = len(prepared), grids.dz
+    base, bounds, fns, filled_obs = [], [], [], []
+    for s, (obs, _, _) in enumerate(prepared):
+        arr = psets[s].array()
+        names = psets[s].columns()
+        nx = len(extra)
+        core = {nm: arr[:, i] for i, nm in enumerate(names[:len(names) - nx])}
+        pairs = [(core['lperc'], core['rperc'])]
+        for k in range(len(probs) - 1):
+            pairs.append((arr[:, arr.shape[1] - nx + 2 * k],
+                          arr[:, arr.shape[1] - nx + 2 * k + 1]))
+        fn = 0
+        if obs.array().shape[0] < dz:
+            obs, fn = fill_station(obs, core['mean'], grids.zi,
+                                   grids.zi + grids.dz, grids.cellz, header)
+        base.append(core)
+        bounds.append(pairs)
+        fns.append(fn)
+        filled_obs.append(obs)
+    nodata = prepared[0][0].nodata if prepared else -999.9
+    out = {}
+    for k, p in enumerate(probs):
+        cols = [np.empty((S, dz)) for _ in range(7)]
+        locals_k = []
+        for s, obs in enumerate(filled_obs):
+            local = dict(base[s])
+            local['lperc'], local['rperc'] = bounds[s][k]
+            locals_k.append(local)
+            fa, fb, fc = _fix_columns(method, local, local)
+            cols[0][s] = obs.array()[:, obs.columns().index('clim')]
+            cols[1][s] = local['mean']
+            cols[2][s] = local['lperc']
+            cols[3][s] = local['rperc']
+            cols[4][s] = fa
+            cols[5][s] = fa if fb is None else fb
+            cols[6][s] = fa if fc is None else fc
+        filled, homog, flagcol, det = _capi.detect(
+            *cols, method=method, thr=float(skewness or 0.0), nodata=nodata,
+            device=grids.device, stream=stream)
+        res = []
+        for s, obs in enumerate(filled_obs):
+            work = gr.PointSet(obs.name, obs.nodata, obs.nvars, list(obs.varnames),
+                               obs.array())
+            work.set_array(work.array(), obs.row_index())
+            hom, dn = _finish(work, locals_k[s], None, method, skewness,
+                              (filled[s], homog[s], flagcol[s], det[s]), flag,
+                              optional_stats, grids, locs[s], rad)
+            res.append((hom, dn, fns[s] + prepared[s][2]))
+        out[p] = res
+    return out
+
+
 def fill_station(pset_file, values, time_min, time_max, time_step=1,
                  header=True):
     """Expand an incomplete station series to every time step of the grid,

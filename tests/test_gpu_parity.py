@@ -627,3 +627,29 @@ def test_moments_only_kernel_with_outlier_in_first_rows():
     close(out[2], ref['varmap'])
     close(out[3], ref['stdmap'])
     close(out[1], ref['skewmap'], rtol=1e-4, atol=2e-4)
+
+
+@pytest.mark.parametrize('method', ['mean', 'median', 'skewness'])
+def test_detect_sweep_equals_detect_many_per_probability(method):
+    """One reduction of the station columns serves every detection
+    probability: detect_sweep must reproduce detect_many prob by prob."""
+    dims, first, cells = [20, 16, 12], [0.0, 0.0, 1990], [100.0, 100.0, 1]
+    R = 120
+    grids = gr.GridFiles.from_synthetic(77, R, dims, first, cells, ND)
+    stations = synth.stations(77, 6, R, dims, first, cells)
+    cols = ['x', 'y', 'time', 'station', 'clim']
+
+    def obs_list():
+        return [gr.PointSet('cand%d' % i, ND, 5, list(cols),
+                            np.array(s['obs'], dtype=np.float64))
+                for i, s in enumerate(stations)]
+    probs = [0.90, 0.925, 0.95, 0.975, 0.99]
+    kw = dict(method=method, skewness=0.5 if method == 'skewness' else None)
+    sweep = hmg.detect_sweep(grids, obs_list(), probs, **kw)
+    for p in probs:
+        ref = hmg.detect_many(grids, obs_list(), prob=p, **kw)
+        for (h1, d1, m1), (h2, d2, m2) in zip(sweep[p], ref):
+            assert (d1, m1) == (d2, m2)
+            assert h1.columns() == h2.columns()
+            assert np.array_equal(h1.array(), h2.array(), equal_nan=True)
+    grids.dump()
