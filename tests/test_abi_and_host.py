@@ -148,6 +148,29 @@ def test_fill_station_matches_oracle():
     assert np.array_equal(got.values.values, exp.values)
 
 
+@pytest.mark.parametrize('years', [
+    [1990, 1991, 1993, 1996],            # regular: increasing, on the axis
+    [1991, 1990, 1993],                  # out of order: the merge walk stalls
+    [1990, 1992, 1992, 1995],            # duplicate year
+    [1989, 1991, 1994],                  # a year before the axis
+    [1990, 1993, 2005],                  # a year beyond the axis
+    [1992.5, 1994],                      # off the axis
+])
+def test_fill_station_irregular_series_follow_the_reference_walk(years):
+    """The vectorised fill_station must give what the reference's merge walk
+    (homog.py:279-337, restated in the oracle) gives, also for series the walk
+    handles oddly (it never skips an observed row it cannot match)."""
+    cols = ['x', 'y', 'time', 'station', 'clim']
+    rows = np.array([[3.0, 4.0, y, 7.0, 100.0 + i] for i, y in enumerate(years)])
+    df = pd.DataFrame(rows, columns=cols)
+    fill = np.arange(8) * 10.0 + 1
+    ps = gr.PointSet('c', -999.9, 5, list(cols), df.copy())
+    got, n = hmg.fill_station(ps, fill, 1990, 1998, 1)
+    exp, m = O.fill_station(df, fill, 1990, 1998, 1)
+    assert n == m
+    assert np.array_equal(got.values.values, exp.values)
+
+
 def test_take_candidate_update_station_roundtrip():
     cols = ['x', 'y', 'time', 'station', 'clim']
     rows = [[0, 0, t, s, 10.0 * s + t] for s in (1, 2, 3) for t in range(4)]
