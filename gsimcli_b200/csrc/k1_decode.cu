@@ -179,7 +179,9 @@ __device__ __forceinline__ unsigned k1_movemask(unsigned hibits) {
 }
 
 __device__ __forceinline__ bool parse_fixed_fast(const unsigned char* p, int W, float* out) {
-    const unsigned addr = static_cast<unsigned>(__cvta_generic_to_shared(p));
+    // (only the low address bits matter: shared and global windows are both
+    // 4-byte aligned in the generic address space)
+    const unsigned addr = static_cast<unsigned>(reinterpret_cast<uintptr_t>(p));
     const unsigned sh = (addr & 3u) * 8u;
     const unsigned* wp = reinterpret_cast<const unsigned*>(p - (addr & 3u));
     unsigned w[5];
@@ -395,9 +397,13 @@ k1_decode_general(const char* __restrict__ text, long long nbytes,
     const long long start = fl == 0 ? 0 : static_cast<long long>(line_end[fl - 1]) + 1;
     const long long end = fl < n_newlines ? static_cast<long long>(line_end[fl]) : nbytes;
     float val;
+    const unsigned char* lp = reinterpret_cast<const unsigned char*>(text) + start;
+    const int len = static_cast<int>(end - start);
+    // short lines take the register fast path too; its 5 aligned word loads may
+    // reach up to 7 bytes past the line, so stay clear of the end of the text
     bool ok = (start <= end) && (end - start < 4096) &&
-              parse_float(reinterpret_cast<const unsigned char*>(text) + start,
-                          static_cast<int>(end - start), &val);
+              ((len >= 1 && len <= 16 && start + 24 <= nbytes && parse_fixed_fast(lp, len, &val)) ||
+               parse_float(lp, len, &val));
     if (ok) out[i] = val;
     else atomicMin(reinterpret_cast<unsigned long long*>(bad_line),
                    static_cast<unsigned long long>(i));
