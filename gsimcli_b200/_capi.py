@@ -76,6 +76,7 @@ SIGNATURES = {
                              C.c_int, C.c_int, C.c_double, C.c_double, c_vp,
                              c_vp, c_vp, c_vp, C.c_int, C.c_int, c_vp]),
     'gsb_debug_cs_counters': (C.c_int, [c_vp, C.c_int]),
+    'gsb_debug_k2_flagged': (C.c_int, [c_vp, C.POINTER(C.c_int)]),
 }
 
 
@@ -175,6 +176,12 @@ class Stack(object):
 
     def set_option(self, key, value):
         check(lib().gsb_stack_set_option(self.handle, key.encode(), int(value)))
+
+    def k2_flagged(self):
+        """Tiles of the last stats_grid call redone by the counting-sort kernel."""
+        n = C.c_int(0)
+        check(lib().gsb_debug_k2_flagged(self.handle, C.byref(n)))
+        return n.value
 
     def device_ptr(self):
         p = c_vp()
@@ -321,6 +328,14 @@ def detect(clim, mean, lperc, rperc, fix_a, fix_b=None, fix_c=None,
     S, dz = arrs[0].shape
     fb = None if fix_b is None else np.ascontiguousarray(fix_b, np.float64)
     fc = None if fix_c is None else np.ascontiguousarray(fix_c, np.float64)
+    # the library reads S*dz doubles from every array: a shorter one would be
+    # over-read.  The reference fails the same way, in pandas
+    # (`meanvalues.index = obs.values.index`, homog.py:197): ValueError.
+    for a in arrs[1:] + [x for x in (fb, fc) if x is not None]:
+        if a.shape != (S, dz):
+            raise ValueError(
+                'Length mismatch: Expected axis has {0} elements, new values '
+                'have {1} elements'.format(a.shape[-1] if a.ndim else 0, dz))
     filled = np.empty((S, dz))
     homog = np.empty((S, dz))
     flag = np.empty((S, dz))

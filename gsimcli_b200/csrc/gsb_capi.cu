@@ -171,6 +171,14 @@ int gsb_stack_create(int device, int64_t R, int64_t N, gsb_stack** out) {
         delete s;
         return GSB_ENOMEM;
     }
+    e = cudaMalloc(&s->k2_flags, (size_t)(s->pitch / 32 + 4) * sizeof(int));
+    if (e == cudaSuccess) e = cudaMemset(s->k2_flags, 0, sizeof(int));
+    if (e != cudaSuccess) {
+        gsb_set_error("cannot allocate the K2 tile list: %s", cudaGetErrorString(e));
+        cudaFree(s->data);
+        delete s;
+        return GSB_ENOMEM;
+    }
     cudaEventCreate(&s->ev0);
     cudaEventCreate(&s->ev1);
     int rc = make_tmap(s);
@@ -183,6 +191,7 @@ int gsb_stack_destroy(gsb_stack* s) {
     if (!s) return GSB_OK;
     cudaSetDevice(s->device);
     if (s->data) cudaFree(s->data);
+    if (s->k2_flags) cudaFree(s->k2_flags);
     if (s->scratch) cudaFree(s->scratch);
     if (s->stage) cudaFree(s->stage);
     if (s->pinned) cudaFreeHost(s->pinned);
@@ -208,8 +217,30 @@ int gsb_stack_set_option(gsb_stack* s, const char* key, int64_t value) {
         s->k2_sm_reserve = (int)value;
         return GSB_OK;
     }
+    if (strcmp(key, "k2_algo") == 0) {
+        GSB_REQUIRE(value >= 0 && value <= 3, "k2_algo must be 0..3");
+        s->k2_algo = (int)value;
+        return GSB_OK;
+    }
+    if (strcmp(key, "k2_nw") == 0) {
+        GSB_REQUIRE(value == 0 || value == 16 || value == 32, "k2_nw must be 0, 16 or 32");
+        s->k2_nw = (int)value;
+        return GSB_OK;
+    }
+    if (strcmp(key, "k2_stats") == 0) {
+        s->k2_stats = value != 0;
+        return GSB_OK;
+    }
     gsb_set_error("unknown option '%s'", key);
     return GSB_EINVAL;
+}
+
+int gsb_debug_k2_flagged(gsb_stack* s, int* count) {
+    GSB_REQUIRE(s && count, "NULL argument");
+    *count = 0;
+    GSB_CUDA(cudaSetDevice(s->device));
+    GSB_CUDA(cudaMemcpy(count, s->k2_flags, sizeof(int), cudaMemcpyDeviceToHost));
+    return GSB_OK;
 }
 
 int gsb_stack_device_ptr(const gsb_stack* s, void** dptr) {

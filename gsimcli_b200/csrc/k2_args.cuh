@@ -16,6 +16,7 @@ struct K2Args {
     long long skip;    // leading columns of tile 0 that precede the requested range
     float* out;        // plane 0, column n0 (may point `skip` elements before the buffer)
     long long out_pitch;
+    const int* tile_list;   // counting-sort kernel only: [0] count, [1 + k] tile (NULL = all tiles)
     unsigned char kind[GSB_MAX_PLANES];
     double q[GSB_MAX_PLANES];
 };
@@ -30,3 +31,7 @@ struct K2Args {
 
 int gsb_launch_k2_csort(gsb_stack* s, const K2Args& args, int ipt, int grid, bool mode,
                         int halo, cudaStream_t st);
+// register-tile kernel (k2_grid_rsel.cu); tiles it cannot finish exactly are
+// appended to d_flagged ([0] count, [1 + k] tile) for the counting-sort kernel
+int gsb_launch_k2_rsel(gsb_stack* s, const K2Args& args, int grid, bool mode, int nw,
+                       int* d_flagged, cudaStream_t st);

@@ -221,8 +221,14 @@ __global__ void __launch_bounds__(128) k3_detect_kernel(const __grid_constant__ 
         // homog.py:200-201 -- NaN observations take the local mean
         if (c != c) c = a.mean[e];
         const double lo = a.lperc[e], hi = a.rperc[e];
-        // homog.py:204 -- ~between(lperc, rperc), inclusive; NaN compares False
-        const bool inside = (c >= lo) && (c <= hi);
+        // homog.py:204 -- ~between(lperc, rperc), inclusive; NaN compares False.
+        // The bounds come from float32 realization values, the observation from
+        // float64 text: an observation that TIES a bound in the reference (both
+        // parsed from the same decimal, e.g. a DSS clamp value 0.7) must tie here
+        // too, so the observation is compared at the stack's precision
+        // (f32(0.7) == f32(0.7), whereas 0.7 > f32(0.7) would flag it).
+        const double cq = static_cast<double>(static_cast<float>(c));
+        const bool inside = (cq >= lo) && (cq <= hi);
         const bool hw = !inside;
         double fix;
         switch (a.method) {
@@ -230,7 +236,7 @@ __global__ void __launch_bounds__(128) k3_detect_kernel(const __grid_constant__ 
             fix = (a.fix_c[e] > a.thr) ? a.fix_a[e] : a.fix_b[e];
             break;
         case GSB_METHOD_PERCENTILE:    // np.where(clim > rperc, rperc', lperc')
-            fix = (c > hi) ? a.fix_a[e] : a.fix_b[e];
+            fix = (cq > hi) ? a.fix_a[e] : a.fix_b[e];
             break;
         default:
             fix = a.fix_a[e];

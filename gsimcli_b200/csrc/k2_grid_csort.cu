@@ -159,13 +159,19 @@ k2_csort_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant_
     uint32_t* H = reinterpret_cast<uint32_t*>(A);
     auto idx = [](int p) { return p + (p >> LOGI); };
 
+    // tiles: all of [0, ntiles), or the ones listed by the register-tile kernel
+    // (k2_grid_rsel.cu) as "could not be finished exactly": [0] count, [1 + k] tile
+    const long long nt = a.tile_list ? static_cast<long long>(a.tile_list[0]) : a.ntiles;
+    auto phys = [&](long long li) -> long long {
+        return a.tile_list ? static_cast<long long>(a.tile_list[1 + li]) : li;
+    };
     if (threadIdx.x == 0) {
         *readers = 0u;
         *ticket = 0u;
         gsb_mbar_init(full, 1);
         gsb_fence_barrier_init();
         gsb_prefetch_tmap(&tmap);
-        if (blockIdx.x < a.ntiles) issue_tile(blockIdx.x);
+        if (blockIdx.x < nt) issue_tile(phys(blockIdx.x));
     }
     // left halo = -INF forever; histogram zero for the first column
     for (int i = lane; i < LPAD; i += 32) A[-1 - i] = -INF;
@@ -201,8 +207,9 @@ k2_csort_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant_
             tk = __shfl_sync(FULL, tk, 0);
             const long long seq = tk >> 5;
             const int c = static_cast<int>(tk & 31u);
-            const long long tile = blockIdx.x + seq * gridDim.x;
-            if (tile >= a.ntiles) break;
+            const long long li = blockIdx.x + seq * gridDim.x;
+            if (li >= nt) break;
+            const long long tile = phys(li);
             if (a.lockstep) {
                 const long long t0 = clock64();
                 gsb_mbar_wait(full, static_cast<uint32_t>(seq & 1));
@@ -236,8 +243,8 @@ k2_csort_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant_
                 __threadfence_block();
                 if (atomicAdd(readers, 1u) == 31u) {
                     *readers = 0u;
-                    const long long nxt = tile + gridDim.x;
-                    if (nxt < a.ntiles) issue_tile(nxt);
+                    const long long nxt = li + gridDim.x;
+                    if (nxt < nt) issue_tile(phys(nxt));
                 }
             }
 
@@ -248,18 +255,22 @@ k2_csort_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant_
             // float32 shifted sums need
             float piv, S1, S2, S3, lo, hi;
             {
-                // median of the first three valid values among the first 32
-                // realizations: one outlier among them cannot become the pivot
-                const uint32_t okm = __ballot_sync(FULL, xs[0] < INF);
+                // the element, among the first 32 realizations, nearest to their
+                // mean: an element (a constant column gives d == 0 exactly) and
+                // within a fraction of sigma of the column mean.  The float32
+                // shifted sums lose |pivot - mean| / sigma digits in the third
+                // moment: a pivot taken blindly (first / median of three elements)
+                // sat 4 sigma out on skewed columns and cost 5e-5 in the skewness.
+                const bool ok0 = xs[0] < INF;
+                const uint32_t okm = __ballot_sync(FULL, ok0);
                 const bool have_piv = okm != 0u;
-                const uint32_t m1 = okm & (okm - 1u), m2 = m1 & (m1 - 1u);
-                const int l0 = have_piv ? __ffs(okm) - 1 : 0;
-                const int l1 = m1 ? __ffs(m1) - 1 : l0;
-                const int l2 = m2 ? __ffs(m2) - 1 : l0;
-                const float c0 = __shfl_sync(FULL, xs[0], l0);
-                const float c1 = __shfl_sync(FULL, xs[0], l1);
-                const float c2 = __shfl_sync(FULL, xs[0], l2);
-                const float cand = fmaxf(fminf(c0, c1), fminf(fmaxf(c0, c1), c2));
+                const float m0 = cs_warp_sum(ok0 ? xs[0] : 0.f) / static_cast<float>(__popc(okm));
+                const float dist = ok0 ? fabsf(xs[0] - m0) : INF;      // NaN when the sum overflowed
+                const uint32_t dkey = (dist == dist) ? __float_as_uint(dist) : 0x7f800000u;
+                const uint32_t dmin = __reduce_min_sync(FULL, dkey);
+                const uint32_t who = __ballot_sync(FULL, dkey == dmin && ok0);
+                const int lsel = who ? __ffs(who) - 1 : (have_piv ? __ffs(okm) - 1 : 0);
+                const float cand = __shfl_sync(FULL, xs[0], lsel);
                 piv = have_piv ? cand : 0.f;
                 float mn = INF, mx = have_piv ? cand : -INF;
                 uint64_t s1 = 0, s2 = 0, s3 = 0;
@@ -409,22 +420,21 @@ k2_csort_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant_
                 const float fnan = __int_as_float(0x7fc00000);
                 const float fn = static_cast<float>(nc);
                 const double d1 = static_cast<double>(S1), d2 = static_cast<double>(S2);
-                const float delta = __fdividef(S1, fn);
+                const float delta = __fdiv_rn(S1, fn);
                 const double dd = static_cast<double>(delta);
                 const bool constant = (S2 == 0.f);
                 const float m2 = constant ? 0.f : fmaxf(static_cast<float>(d2 - d1 * dd), 0.f);
                 const float m3 = constant ? 0.f : static_cast<float>(
                     static_cast<double>(S3) - 3.0 * dd * d2 + 2.0 * d1 * dd * dd);
                 const float mean = piv + delta;
-                const float var = __fdividef(m2, fn - 1.f);
+                const float var = __fdiv_rn(m2, fn - 1.f);
                 const float sd = sqrtf(var);
                 st_mean = nc > 0 ? mean : fnan;
                 st_var = nc > 1 ? var : fnan;
                 st_sd = nc > 1 ? sd : fnan;
-                st_cv = nc > 1 ? __fdividef(sd, mean) * 100.f : fnan;
-                const float r2 = rsqrtf(m2);
+                st_cv = nc > 1 ? __fdiv_rn(sd, mean) * 100.f : fnan;
                 st_skew = nc < 3 ? fnan : (m2 == 0.f) ? 0.f
-                        : __fdividef(fn * sqrtf(fn - 1.f), fn - 2.f) * (m3 * r2 * r2 * r2);
+                        : __fdiv_rn(fn * sqrtf(fn - 1.f), fn - 2.f) * __fdiv_rn(m3, m2 * sqrtf(m2));
             }
             float w[W];
             if (!allsame) {
@@ -713,12 +723,7 @@ extern "C" int gsb_debug_cs_counters(unsigned long long* out, int reset) {
 
 int gsb_launch_k2_csort(gsb_stack* s, const K2Args& args, int ipt, int grid, bool mode,
                         int halo, cudaStream_t st) {
-    if (halo == 12)
-        return mode ? cs_launch_ipt<true, 12>(s, args, ipt, grid, st)
-                    : cs_launch_ipt<false, 12>(s, args, ipt, grid, st);
-    if (halo == 8)
-        return mode ? cs_launch_ipt<true, 8>(s, args, ipt, grid, st)
-                    : cs_launch_ipt<false, 8>(s, args, ipt, grid, st);
+    (void)halo;      // one window halo (10) is built: 8 and 12 measured slower
     return mode ? cs_launch_ipt<true, 10>(s, args, ipt, grid, st)
                 : cs_launch_ipt<false, 10>(s, args, ipt, grid, st);
 }

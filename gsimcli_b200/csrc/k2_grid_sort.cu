@@ -593,14 +593,8 @@ int gsb_launch_k2_sort(gsb_stack* s, const GsbPlanes& pl, float nodata, int64_t 
     args.nchunks = static_cast<int>((s->R + 31) / 32);
     args.nplanes = pl.n;
     args.nodata = nodata;
-    // GSB_K2_LOCKSTEP: block barriers inside the bitonic kernel (experiment);
-    // GSB_K2_STATS: diagnostic counters of the counting-sort kernel
-    // (gsb_debug_cs_counters).  Both travel in the same field.
-    const char* ls = getenv("GSB_K2_LOCKSTEP");
-    const char* sts = getenv("GSB_K2_STATS");
-    args.lockstep = (ls ? atoi(ls) : 0) | (sts ? atoi(sts) : 0);
-    const char* sk = getenv("GSB_K2_SKEW");
-    args.skew = sk ? atoi(sk) : 1;
+    args.lockstep = s->k2_stats;      // diagnostic counters of the counting-sort kernel
+    args.skew = 1;
     const int64_t head = n0 & 3;
     args.n0 = n0 - head;
     args.nn = nn + head;
@@ -614,19 +608,25 @@ int gsb_launch_k2_sort(gsb_stack* s, const GsbPlanes& pl, float nodata, int64_t 
     const int ctas = s->sm_count - s->k2_sm_reserve;
     const int grid = static_cast<int>(args.ntiles < ctas ? args.ntiles : ctas);
     if (grid <= 0) return GSB_OK;
-    // counting-sort kernel for the deep columns (default for R > 32); the
-    // register bitonic sort below stays the kernel for shallow ones
-    const char* alg = getenv("GSB_K2_ALGO");
-    const bool want_cs = alg ? (strcmp(alg, "csort") == 0) : (ipt >= 2);
-    if (want_cs && ipt >= 2) {
-        const char* hl = getenv("GSB_K2_HALO");
-        return gsb_launch_k2_csort(s, args, ipt, grid, pl.need_mode != 0, hl ? atoi(hl) : 10, st);
+    // R > 32: the counting-sort kernel (k2_grid_csort.cu).  R <= 32: the register
+    // bitonic sort below.  `k2_algo` (gsb_stack_set_option, tests and profiling
+    // only) selects another of the three implementations so that the parity
+    // suite can cross-check them: 2 = bitonic for every R, 3 = the register-tile
+    // kernel (k2_grid_rsel.cu: measured equal to the counting sort without the
+    // mode plane and 2.3x slower with it -- DESIGN.md section 8), whose flagged
+    // tiles (bin map collapsed by an outlier, heavy ties, range overflow) are
+    // redone by the counting-sort kernel on the same stream.
+    const int algo = s->k2_algo;
+    if (ipt >= 2 && algo != 2) {
+        if (algo != 3)
+            return gsb_launch_k2_csort(s, args, ipt, grid, pl.need_mode != 0, 10, st);
+        int* d_flagged = s->k2_flags;        // ntiles <= pitch / 32 + 1 (unaligned n0)
+        GSB_CUDA(cudaMemsetAsync(d_flagged, 0, sizeof(int), st));
+        int rc = gsb_launch_k2_rsel(s, args, grid, pl.need_mode != 0, s->k2_nw == 16 ? 16 : 32, d_flagged, st);
+        if (rc) return rc;
+        args.tile_list = d_flagged;
+        return gsb_launch_k2_csort(s, args, ipt, grid, pl.need_mode != 0, 10, st);
     }
-    const char* cp = getenv("GSB_K2_CPW");
-    const int cpw = cp ? atoi(cp) : 2;
-    if (cpw == 2)
-        return pl.need_mode ? launch_ipt<true, 2>(s, args, ipt, grid, st)
-                            : launch_ipt<false, 2>(s, args, ipt, grid, st);
-    return pl.need_mode ? launch_ipt<true, 4>(s, args, ipt, grid, st)
-                        : launch_ipt<false, 4>(s, args, ipt, grid, st);
+    return pl.need_mode ? launch_ipt<true, 2>(s, args, ipt, grid, st)
+                        : launch_ipt<false, 2>(s, args, ipt, grid, st);
 }

@@ -4,8 +4,8 @@
 // without median/percentiles: a pure HBM-bound stream.  One thread owns one
 // node and walks the R rows; a warp reads 128 contiguous bytes of every row
 // (the stack is realization-major, so no transpose and no shared memory).
-// Shifted one-pass sums around a pivot (median of the first three valid values
-// among the first 16 rows, which stay in registers so nothing is re-read): differences and products in float32,
+// Shifted one-pass sums around a pivot (the valid value nearest to the mean of
+// the first 16 rows, which stay in registers so nothing is re-read): differences and products in float32,
 // 16-row partial sums flushed into float64 accumulators.  Algorithmic traffic:
 // 4 B per node-realization + 4 B per node and output map.
 #include "gsb_common.cuh"
@@ -42,21 +42,35 @@ k2_moments_kernel(const __grid_constant__ KmArgs a) {
         const float* col = a.data + a.n0 + node;
         // ---- head rows: pivot
         float head[KM_HEAD];
-        float c0 = 0.f, c1 = 0.f, c2 = 0.f;
+        float hsum = 0.f;
         int hc = 0;
         const int nh = a.R < KM_HEAD ? a.R : KM_HEAD;
 #pragma unroll
         for (int r = 0; r < KM_HEAD; ++r) {
             head[r] = (r < nh) ? ldg_stream(col + r * a.pitch) : a.nodata;
             const bool ok = (head[r] == head[r]) && (head[r] != a.nodata);
-            if (ok) {
-                if (hc == 0) c0 = head[r]; else if (hc == 1) c1 = head[r]; else if (hc == 2) c2 = head[r];
-                ++hc;
+            hsum += ok ? head[r] : 0.f;
+            hc += ok ? 1 : 0;
+        }
+        // pivot: the valid head value nearest to the head mean -- an element (a
+        // constant column gives d == 0 exactly), never an outlier, and within a
+        // fraction of sigma of the column mean (the float32 shifted sums lose
+        // |pivot - mean| / sigma digits in the third moment)
+        float piv = 0.f;
+        {
+            const float hm = hsum / static_cast<float>(hc);
+            float bestd = __int_as_float(0x7f800000);
+            bool found = false;
+#pragma unroll
+            for (int r = 0; r < KM_HEAD; ++r) {
+                const bool ok = (head[r] == head[r]) && (head[r] != a.nodata);
+                const float d = fabsf(head[r] - hm);
+                const bool take = ok && (!found || d < bestd);     // NaN distances: first valid one
+                piv = take ? head[r] : piv;
+                bestd = take ? d : bestd;
+                found = found || ok;
             }
         }
-        // pivot: median of the first three valid head values (an element, and one
-        // outlier among them cannot become the pivot), else the first valid one
-        float piv = hc >= 3 ? fmaxf(fminf(c0, c1), fminf(fmaxf(c0, c1), c2)) : c0;
         double S1 = 0.0, S2 = 0.0, S3 = 0.0;
         int n = 0;
         float vmin = __int_as_float(0x7f800000), vmax = __int_as_float(0xff800000);

@@ -166,6 +166,7 @@ def detect(grids, obs_file, rad=0, method='mean', prob=0.95, skewness=None,
     if obs.array().shape[0] < grids.dz:
         obs, fn = fill_station(obs, meanvalues, grids.zi, grids.zi + grids.dz,
                                grids.cellz, header)
+    _check_series(obs, grids.dz)
     if method == 'percentile' and percentile != prob:
         grids.reset_read()
         vline_perc = _table(grids.stats_area(obs_xy, rad, lperc=True,
@@ -215,6 +216,7 @@ def detect_many(grids, obs_list, rad=0, method='mean', prob=0.95,
         if obs.array().shape[0] < dz:
             obs, fn = fill_station(obs, local['mean'], grids.zi,
                                    grids.zi + grids.dz, grids.cellz, header)
+        _check_series(obs, dz)
         fns.append(fn)
         obs_filled.append(obs)
         fa, fb, fc = _fix_columns(method, local, vperc[s])
@@ -275,6 +277,7 @@ def detect_sweep(grids, obs_list, probs, rad=0, method='mean', skewness=None,
         if obs.array().shape[0] < dz:
             obs, fn = fill_station(obs, core['mean'], grids.zi,
                                    grids.zi + grids.dz, grids.cellz, header)
+        _check_series(obs, dz)
         base.append(core)
         bounds.append(pairs)
         fns.append(fn)
@@ -310,6 +313,17 @@ def detect_sweep(grids, obs_list, probs, rad=0, method='mean', skewness=None,
             res.append((hom, dn, fns[s] + prepared[s][2]))
         out[p] = res
     return out
+
+
+def _check_series(obs, dz):
+    """The filled series must have one row per grid time step.  The reference
+    fails in pandas when it does not (`meanvalues.index = obs.values.index`,
+    homog.py:197, raises ValueError: Length mismatch); same exception here,
+    before any device buffer is sized from the wrong length."""
+    rows = obs.array().shape[0]
+    if rows != dz:
+        raise ValueError('Length mismatch: Expected axis has {0} elements, new '
+                         'values have {1} elements'.format(dz, rows))
 
 
 def fill_station(pset_file, values, time_min, time_max, time_step=1,

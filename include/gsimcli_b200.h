@@ -96,6 +96,10 @@ int gsb_stack_info(const gsb_stack* s, int64_t* R, int64_t* N, int64_t* pitch,
  * free (default 0) so that station-column / detect launches on another stream
  * run concurrently with it instead of queueing behind its persistent CTAs. */
 int gsb_stack_set_option(gsb_stack* s, const char* key, int64_t value);
+/* diagnostic: number of 32-node tiles of the last gsb_stats_grid call on this
+ * stack that the register-tile kernel handed to the counting-sort kernel
+ * (synchronises the device). */
+int gsb_debug_k2_flagged(gsb_stack* s, int* count);
 /* raw device pointer of row 0 (float32, row pitch `pitch` elements): the
  * tensor handle torch wraps for NCCL plumbing.  Never dereference on host. */
 int gsb_stack_device_ptr(const gsb_stack* s, void** dptr);

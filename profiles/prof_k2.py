@@ -14,11 +14,18 @@ R = int(sys.argv[1]) if len(sys.argv) > 1 else 1000
 dims = [int(x) for x in (sys.argv[2] if len(sys.argv) > 2 else '200,200,10').split(',')]
 kind = sys.argv[3] if len(sys.argv) > 3 else 'mode'
 reps = int(sys.argv[4]) if len(sys.argv) > 4 else 3
-N = int(os.environ.get('GSB_PROF_N', np.prod(dims)))
+N = int(os.environ.get("GSB_PROF_N", np.prod(dims)))
 NODE0 = int(os.environ.get('GSB_PROF_NODE0', 0))
 QS = [round(0.05 * k, 2) for k in range(1, 20)]
 stack = _capi.Stack(R, N)
 stack.synth_fill(1003, dims, NODE0, -999.9)
+# test-only kernel selection: register tile (32 / 16 warps), counting sort, bitonic
+ALGO = os.environ.get('GSB_PROF_ALGO', 'csort')
+k2_algo, k2_nw = {'rsel': (3, 0), 'rsel16': (3, 16), 'csort': (0, 0), 'bitonic': (2, 0)}[ALGO]
+stack.set_option('k2_algo', k2_algo)
+stack.set_option('k2_nw', k2_nw)
+if os.environ.get('GSB_K2_STATS'):
+    stack.set_option('k2_stats', 1)
 flags = _capi.MEAN | _capi.SKEW | _capi.VAR | _capi.STD | _capi.COEFVAR
 qs = None
 if kind == 'refapi':          # the reference's stats(): moments + median + percentile pair
@@ -40,8 +47,8 @@ for i in range(reps):
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1)
     gbs = (4.0 * R * N + 4.0 * npl * N) / ms / 1e6
-    print('%s R=%d N=%d planes=%d: %.3f ms  %.1f GB/s  %.3e node-real/s' % (
-        kind, R, N, npl, ms, gbs, R * N / ms * 1e3))
+    print('%s %s R=%d N=%d planes=%d: %.3f ms  %.1f GB/s  %.3e node-real/s  flagged tiles %d' % (
+        ALGO, kind, R, N, npl, ms, gbs, R * N / ms * 1e3, stack.k2_flagged()))
 if os.environ.get('GSB_K2_STATS'):
     import ctypes
     buf = (ctypes.c_ulonglong * 8)()

@@ -1,5 +1,6 @@
-"""Randomised cross-check of the two K2 sort kernels (counting sort vs register
-bitonic): order statistics and mode must agree bit for bit on every column of
+"""Randomised cross-check of the K2 sort kernels (register tile, 32 and 16 warps,
+vs counting sort vs register bitonic; forced through the test-only stack options
+k2_algo / k2_nw): order statistics and mode must agree bit for bit on every column of
 many random stacks (mixtures of smooth, tied, clamped, clustered and outlier
 columns, random R and missing-value rates).  python profiles/stress_k2.py [rounds]"""
 import os, sys
@@ -42,22 +43,25 @@ for it in range(rounds):
     stack.upload(st32)
     outs = {}
     pp = float(rng.choice([0.9, 0.95, 0.5]))
-    for algo in ('csort', 'bitonic'):
-        os.environ['GSB_K2_ALGO'] = algo
+    for algo, (k2_algo, k2_nw) in (('rsel', (3, 0)), ('rsel16', (3, 16)), ('csort', (0, 0)), ('bitonic', (2, 0))):
+        stack.set_option('k2_algo', k2_algo)
+        stack.set_option('k2_nw', k2_nw)
         outs[algo] = stack.stats_grid(flags, pp, qs, ND)
     stack.close()
-    a, b = outs['csort'], outs['bitonic']
+    b = outs['bitonic']
     # planes: mean, median, skew, var, std, coefvar, lperc, rperc, q..., mode
-    exact = [1, 6, 7] + list(range(8, a.shape[0]))
-    same = (a[exact].view(np.int32) == b[exact].view(np.int32)) | (np.isnan(a[exact]) & np.isnan(b[exact]))
-    nbad = int((~same).sum())
+    exact = [1, 6, 7] + list(range(8, b.shape[0]))
     tame = np.isin(kind, [0, 1, 2, 3])       # float32 moments are only comparable without 1e12 outliers / 1e7 offsets
-    mom_ok = np.allclose(a[[0, 3, 4]][:, tame], b[[0, 3, 4]][:, tame], rtol=2e-4, atol=1e-6, equal_nan=True)
-    print('round %2d R=%4d N=%5d nq=%2d miss-classes ok: exact-mismatches=%d moments-close=%s' % (it, R, N, len(qs), nbad, mom_ok), flush=True)
-    if nbad:
-        idx = np.argwhere(~same)[:5]
-        for pl, col in idx:
-            print('   plane', exact[pl], 'col', col, 'kind', kind[col], a[exact[pl], col], b[exact[pl], col])
-        bad += nbad
+    for algo in ('rsel', 'rsel16', 'csort'):
+        a = outs[algo]
+        same = (a[exact].view(np.int32) == b[exact].view(np.int32)) | (np.isnan(a[exact]) & np.isnan(b[exact]))
+        nbad = int((~same).sum())
+        mom_ok = np.allclose(a[[0, 3, 4]][:, tame], b[[0, 3, 4]][:, tame], rtol=2e-4, atol=1e-6, equal_nan=True)
+        print('round %2d R=%4d N=%5d nq=%2d %-6s vs bitonic: exact-mismatches=%d moments-close=%s' % (it, R, N, len(qs), algo, nbad, mom_ok), flush=True)
+        if nbad:
+            idx = np.argwhere(~same)[:5]
+            for pl, col in idx:
+                print('   plane', exact[pl], 'col', col, 'kind', kind[col], a[exact[pl], col], b[exact[pl], col])
+            bad += nbad
 print('TOTAL exact mismatches:', bad)
 sys.exit(1 if bad else 0)

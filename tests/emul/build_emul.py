@@ -1,0 +1,20 @@
+# -*- coding: utf-8 -*-
+"""Builds tests/emul/libk2rsel_emul.so: the host emulation of the K2 register-
+tile kernel (the phases header of the CUDA kernel compiled by g++).  Test
+infrastructure only."""
+import os
+import subprocess
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+SRC = os.path.join(HERE, 'k2_rsel_emul.cpp')
+HDR = os.path.join(HERE, '..', '..', 'gsimcli_b200', 'csrc', 'k2_rsel_phases.cuh')
+LIB = os.path.join(HERE, 'libk2rsel_emul.so')
+
+
+def build(force=False):
+    if (not force and os.path.exists(LIB)
+            and os.path.getmtime(LIB) >= max(os.path.getmtime(SRC), os.path.getmtime(HDR))):
+        return LIB
+    subprocess.run(['g++', '-O2', '-std=c++17', '-ffp-contract=off', '-Wno-unknown-pragmas',
+                    '-shared', '-fPIC', '-o', LIB, SRC], check=True)
+    return LIB

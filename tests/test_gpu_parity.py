@@ -45,12 +45,25 @@ def close(a, b, rtol=1e-5, atol=0.0):
     np.testing.assert_allclose(a, b, rtol=rtol, atol=atol, equal_nan=True)
 
 
-def check_grid(st, p=0.95, percentiles=QS, mode=True, n0=0, nn=None):
+# the three full-grid K2 kernels, forced through the test-only stack options:
+# register tile (default; 32 or 16 warps), counting sort, register bitonic sort
+ALGOS = {'rsel': (3, 0), 'rsel16': (3, 16), 'csort': (0, 0), 'bitonic': (2, 0)}
+
+
+def force_algo(stack, algo):
+    if algo is not None:
+        a, nw = ALGOS[algo]
+        stack.set_option('k2_algo', a)
+        stack.set_option('k2_nw', nw)
+
+
+def check_grid(st, p=0.95, percentiles=QS, mode=True, n0=0, nn=None, algo=None):
     """Full-grid planes of the CUDA path vs the oracle on the same f32 values."""
     st = np.ascontiguousarray(st, dtype=np.float32)
     R, N = st.shape
     nn = N - n0 if nn is None else nn
     stack = _capi.Stack(R, N)
+    force_algo(stack, algo)
     stack.upload(st)
     flags = ALLF | (_capi.MODE if mode else 0)
     out = stack.stats_grid(flags, p, percentiles, ND, n0, nn)
@@ -59,7 +72,7 @@ def check_grid(st, p=0.95, percentiles=QS, mode=True, n0=0, nn=None):
     sigma = np.nanmax(ref['stdmap']) if np.isfinite(ref['stdmap']).any() else 1.0
     close(out[0], ref['meanmap'])
     same_bits(out[1], ref['medianmap'])
-    close(out[2], ref['skewmap'], rtol=1e-4, atol=2e-4)
+    close(out[2], ref['skewmap'], rtol=1e-5, atol=1e-5)     # north_star: 1e-5, floor 1e-5
     close(out[3], ref['varmap'], atol=1e-5 * sigma ** 2 * 1e-3)
     close(out[4], ref['stdmap'], atol=1e-6 * sigma)
     close(out[5], ref['coefvarmap'], atol=1e-6)
@@ -135,12 +148,12 @@ def test_grid_stats_all_R(R):
     check_grid(st)
 
 
-@pytest.mark.parametrize('algo', ['csort', 'bitonic'])
+@pytest.mark.parametrize('algo', ['rsel', 'rsel16', 'csort', 'bitonic'])
 @pytest.mark.parametrize('R', [100, 129, 200, 256, 500, 512, 1000, 1024])
-def test_grid_stats_both_sort_kernels(algo, R, monkeypatch):
-    """The counting-sort kernel (k2_grid_csort.cu) and the register bitonic
-    kernel (k2_grid_sort.cu) must both be exact; GSB_K2_ALGO forces one."""
-    monkeypatch.setenv('GSB_K2_ALGO', algo)
+def test_grid_stats_every_sort_kernel(algo, R):
+    """The register-tile kernel (k2_grid_rsel.cu, 32 and 16 warps), the
+    counting-sort kernel (k2_grid_csort.cu) and the register bitonic kernel
+    (k2_grid_sort.cu) must all be exact; the stack option forces one."""
     dims = [11, 9, 5]
     st = synth.stack(2000 + R, R, dims)
     st[:, 3] = 812.5
@@ -148,14 +161,13 @@ def test_grid_stats_both_sort_kernels(algo, R, monkeypatch):
     st[:, 5] = np.float32(ND)
     st[R // 2, 5] = 640.25
     st[:, 8] = np.where(np.arange(R) % 2 == 0, 500.0, 600.0)
-    check_grid(st)
+    check_grid(st, algo=algo)
 
 
-@pytest.mark.parametrize('algo', ['csort', 'bitonic'])
-def test_grid_stats_adversarial_distributions(algo, monkeypatch):
+@pytest.mark.parametrize('algo', ['rsel', 'rsel16', 'csort', 'bitonic'])
+def test_grid_stats_adversarial_distributions(algo):
     """Distributions that defeat a linear bin map (outliers, clusters, huge
     offsets, heavy ties, first realizations all missing) must stay exact."""
-    monkeypatch.setenv('GSB_K2_ALGO', algo)
     rng = np.random.default_rng(17)
     for R in (200, 1000):
         N = 160
@@ -181,6 +193,7 @@ def test_grid_stats_adversarial_distributions(algo, monkeypatch):
         st32 = st.astype(np.float32)
         R_, N_ = st32.shape
         stack = _capi.Stack(R_, N_)
+        force_algo(stack, algo)
         stack.upload(st32)
         flags = _capi.MEDIAN | _capi.PERC | _capi.MODE
         out = stack.stats_grid(flags, 0.95, QS, ND)
@@ -233,7 +246,7 @@ def test_moments_only_kernel():
         ref = O.grid_stats(st, ND, flags)
         sigma = 150.0
         close(out[0], ref['meanmap'])
-        close(out[1], ref['skewmap'], rtol=1e-4, atol=2e-4)
+        close(out[1], ref['skewmap'], rtol=1e-5, atol=1e-5)
         close(out[2], ref['varmap'], atol=1e-8 * sigma ** 2)
         close(out[3], ref['stdmap'], atol=1e-6 * sigma)
         close(out[4], ref['coefvarmap'], atol=1e-6)
@@ -626,7 +639,7 @@ def test_moments_only_kernel_with_outlier_in_first_rows():
     close(out[0], ref['meanmap'])
     close(out[2], ref['varmap'])
     close(out[3], ref['stdmap'])
-    close(out[1], ref['skewmap'], rtol=1e-4, atol=2e-4)
+    close(out[1], ref['skewmap'], rtol=1e-5, atol=1e-5)
 
 
 @pytest.mark.parametrize('method', ['mean', 'median', 'skewness'])
