@@ -2,23 +2,33 @@
 """Benchmark of the local-PDF + detection hot path (BASELINE.json metric).
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+                    [--config 3|4|5] [--scaling strong|weak]
 
-Workload (BASELINE.json configs[2], the configuration the metric's target is
-quoted on; it fits one B200): 1000 realizations of a 200x200x100 grid, full
-percentile set 5..95 step 5 + mode + moments + median, plus detection with
-median correction at 20 candidate stations.  One "step" = one pass of the hot
-path over the whole stack: K2 (full-grid reduction), K2c (station columns) and
-K3 (detect/correct).  With N > 1 GPUs every rank holds its own block of 100
-time slices of a 200x200x(100 N) grid (weak scaling, node sharding; the only
-exchange is the all-gather of the per-station tables).
+Default workload (BASELINE.json configs[2], the configuration the metric's
+target is quoted on; it fits one B200): 1000 realizations of a 200x200x100
+grid, full percentile set 5..95 step 5 + mode + moments + median, plus detection
+with median correction at 20 candidate stations.  One "step" = one pass of the
+hot path over the whole stack: K2 (full-grid reduction), K2c (station columns),
+the all-gather of the station tables (N > 1) and K3 (detect/correct), ending
+with the station results on the host.
+
+N > 1 GPUs, default ``--scaling strong``: the SAME grid, node-sharded by blocks
+of time slices (rank r holds 100/N layers; each node's realization column stays
+on one GPU, so every order statistic is exact).  ``--scaling weak`` keeps 100
+layers per GPU (a 200x200x(100 N) grid).  The only exchange is the all-gather
+of the per-station tables (NCCL, device buffers).
+
+``--config 4``: GSLIB ASCII decode + stats of 500 realization files from pinned
+host text (K1 + K2).  ``--config 5``: batch homogenisation, 100 networks x 100
+realizations of 80x80x50 with a sweep of 5 detection probabilities, whole
+networks dealt round-robin to the GPUs.
 
 Keys of the JSON line: see the task contract.  ``value`` = node-realizations/s
-with the stack resident in HBM; ``e2e`` = the same through the public API with
-the float32 stack in pinned HOST memory (H2D of the stack in node slabs, each
-slab's reduction and the D2H of its maps overlapped with the next upload -- all
-inside the timed region); ``roofline`` for the dominant kernel (K2) against
-the measured HBM peak; ``cpu_baseline`` = the NumPy oracle on a bounded sample
-on the host cores.
+with the inputs resident in HBM; ``e2e`` = the same through the public API from
+pinned HOST buffers (H2D of the inputs and D2H of the results inside the timed
+region); ``roofline`` for the dominant kernel against the measured HBM peak;
+``cpu_baseline`` = the NumPy oracle on a bounded sample on the host cores;
+``parity`` = the GPU results of this very run checked against the oracle.
 """
 import argparse
 import json
@@ -27,6 +37,7 @@ import subprocess
 import sys
 import threading
 import time
+import zlib
 
 import numpy as np
 
@@ -44,14 +55,30 @@ ND = -999.9
 QS = [round(0.05 * k, 2) for k in range(1, 20)]
 METRIC = 'node-realizations/sec for local-PDF stats + detection'
 UNIT = 'node-realizations/s'
+OCOLS = ['x', 'y', 'time', 'station', 'clim']
 
 
-def workload_name(n_gpus):
+def workload_name(n_gpus, scaling='strong', config=3):
     d = DIMS1
-    return ('{0} realizations of {1}x{2}x{3} grid per GPU ({4} GPU(s), '
-            'node-sharded by time slices), mean/var/std/coefvar/skew/median + '
-            'percentiles 5..95 step 5 + mode, detection + median correction at '
-            '{5} stations').format(R, d[0], d[1], d[2], n_gpus, NSTATIONS)
+    if config == 4:
+        return ('GSLIB ASCII decode (14 B/line) + stats of {0} realization files '
+                '({1}x{2}x{3}) from pinned host buffers, {4} GPU(s), node-sharded')\
+            .format(C4_FILES, d[0], d[1], d[2], n_gpus)
+    if config == 5:
+        return ('batch homogenisation of {0} networks x {1} realizations '
+                '({2}x{3}x{4}), {5} stations each, detection-probability sweep '
+                '{6}, networks round-robin over {7} GPU(s)').format(
+                    C5_NETWORKS, C5_R, C5_DIMS[0], C5_DIMS[1], C5_DIMS[2],
+                    C5_STATIONS, C5_PROBS, n_gpus)
+    if scaling == 'weak':
+        return ('{0} realizations of {1}x{2}x{3} grid per GPU ({4} GPU(s), '
+                'node-sharded by time slices), mean/var/std/coefvar/skew/median + '
+                'percentiles 5..95 step 5 + mode, detection + median correction at '
+                '{5} stations').format(R, d[0], d[1], d[2], n_gpus, NSTATIONS)
+    return ('{0} realizations of {1}x{2}x{3} grid, node-sharded by time slices '
+            'over {4} GPU(s), mean/var/std/coefvar/skew/median + percentiles '
+            '5..95 step 5 + mode, detection + median correction at {5} stations')\
+        .format(R, d[0], d[1], d[2], n_gpus, NSTATIONS)
 
 
 def peaks():
@@ -110,7 +137,9 @@ class ClockSampler(threading.Thread):
                 pass
             self.stop_flag.wait(0.2)
 
-    def summary(self):
+    def finish(self):
+        self.stop_flag.set()
+        self.join(timeout=2)
         if not self.samples:
             return {'sm_mhz': None, 'sm_max_mhz': self.max_mhz, 'reasons': []}
         return {'sm_mhz': float(np.median(self.samples)),
@@ -118,8 +147,11 @@ class ClockSampler(threading.Thread):
 
 
 # ---------------------------------------------------------------- CPU legs
+ORACLE_FLAGS = None
+
+
 def _oracle_chunk(args):
-    seed, dims, nodes = args
+    seed, dims, nodes, keep = args
     from gsimcli_b200 import synth
     from oracle import np_oracle as O
     cols = synth.columns(seed, R, dims, nodes, ND)
@@ -127,30 +159,45 @@ def _oracle_chunk(args):
              | O.FLAG_COEFVAR | O.FLAG_MODE)
     t0 = time.perf_counter()
     res = O.grid_stats(cols, ND, flags, 0.95, QS)
-    return time.perf_counter() - t0, float(np.nansum(res['medianmap']))
+    dt = time.perf_counter() - t0
+    if not keep:
+        return dt, None
+    planes = np.vstack([res['meanmap'], res['medianmap'], res['skewmap'], res['varmap'],
+                        res['stdmap'], res['coefvarmap'], res['percentiles'].T,
+                        res['modemap']])
+    return dt, planes
 
 
-def cpu_sample(dims, nnodes, procs, chunk=8192):
+def cpu_sample(dims, nodes, procs, chunk=8192, keep=False):
     """Time the oracle (``oracle/np_oracle.py``, the NumPy port of the
-    reference's per-node statistics) on ``nnodes`` columns of the workload,
+    reference's per-node statistics) on the columns ``nodes`` of the workload,
     in chunks spread over ``procs`` processes.  The realization values are
     generated in memory outside the timed region (the reference additionally
-    parses text).  Returns (node-realizations/s, seconds of oracle time)."""
+    parses text).  Returns (node-realizations/s, seconds, planes or None);
+    with several processes the seconds are the SCHEDULED wall: oracle compute
+    time dealt over the workers (process start-up and pickling not counted --
+    this favours the CPU arm)."""
     import multiprocessing as mp
-    rng = np.random.default_rng(0)
-    nodes = np.sort(rng.choice(int(np.prod(dims)), size=nnodes, replace=False))
+    nnodes = len(nodes)
     nchunks = max(max(procs, 1) * 2, (nnodes + chunk - 1) // chunk)
     chunks = [c for c in np.array_split(nodes, nchunks) if len(c)]
     if procs > 1:
         with mp.get_context('fork').Pool(procs) as pool:
-            times = pool.map(_oracle_chunk, [(SEED, dims, c) for c in chunks])
-        # oracle compute time scheduled over `procs` workers
-        busy = sum(t for t, _ in times)
-        wall = max(busy / procs, max(t for t, _ in times))
+            outs = pool.map(_oracle_chunk, [(SEED, dims, c, keep) for c in chunks])
+        busy = sum(t for t, _ in outs)
+        wall = max(busy / procs, max(t for t, _ in outs))
     else:
-        times = [_oracle_chunk((SEED, dims, c)) for c in chunks]
-        wall = sum(t for t, _ in times)
-    return nnodes * R / wall, wall
+        outs = [_oracle_chunk((SEED, dims, c, keep)) for c in chunks]
+        wall = sum(t for t, _ in outs)
+    planes = np.hstack([p for _, p in outs]) if keep else None
+    return nnodes * R / wall, wall, planes
+
+
+def sample_nodes(dims, n, lo=0, hi=None):
+    rng = np.random.default_rng(0)
+    hi = int(np.prod(dims)) if hi is None else hi
+    n = min(n, hi - lo)
+    return np.sort(rng.choice(hi - lo, size=n, replace=False)) + lo
 
 
 def run_reference(args):
@@ -160,9 +207,10 @@ def run_reference(args):
     cores = len(os.sched_getaffinity(0))
     dims = list(DIMS1)
     nnodes = int(os.environ.get('GSB_REF_NODES', 65536 * max(1, min(cores, 32))))
+    nodes = sample_nodes(dims, nnodes)
     vals, walls = [], []
     for i in range(args.warmup + args.steps):
-        v, w = cpu_sample(dims, nnodes, cores)
+        v, w, _ = cpu_sample(dims, nodes, cores)
         if i >= args.warmup:
             vals.append(v)
             walls.append(w)
@@ -171,43 +219,129 @@ def run_reference(args):
         'impl': 'reference', 'metric': METRIC, 'value': value, 'unit': UNIT,
         'n_gpus': args.gpus, 'steps': args.steps, 'warmup': args.warmup,
         'ms_per_step': float(np.mean(walls)) * 1e3, 'higher_is_better': True,
-        'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f64',
+        'scaling': args.scaling, 'vs_baseline': None, 'dtype': 'f64',
         'data': 'synthetic',
-        'config': {'workload': workload_name(args.gpus)},
+        'config': {'workload': workload_name(args.gpus, args.scaling, args.config)},
         'cpu_baseline': {
             'value': value, 'unit': UNIT, 'cores': cores, 'kind': 'port',
+            'wall': 'scheduled',
             'sample': ('{0} node columns x {1} realizations per step, NumPy '
-                       'oracle (oracle/np_oracle.py) over {2} processes; the '
-                       'reference itself is Python 2 and cannot run on this '
-                       'box').format(nnodes, R, cores)},
+                       'oracle (oracle/np_oracle.py: vectorised restatement of '
+                       'GridFiles.stats on in-memory values, no text parsing) '
+                       'over {2} processes; wall = oracle compute time dealt '
+                       'over the workers.  The reference itself is Python 2 '
+                       '+ per-node Python loops (about 6e4 node-realizations/s '
+                       'through oracle/refshim.py, BASELINE.md) and cannot run '
+                       'on this box').format(nnodes, R, cores)},
         'e2e': {'value': value, 'unit': UNIT, 'h2d_bytes_per_step': 0,
                 'd2h_bytes_per_step': 0},
     }
     print(json.dumps(line))
 
 
-# ------------------------------------------------------------------ GPU arm
-def run_gpu(args):
+# ------------------------------------------------------------------ helpers
+class Dist(object):
+    def __init__(self):
+        import torch
+        import torch.distributed as td
+        self.torch, self.td = torch, td
+        self.world = int(os.environ.get('WORLD_SIZE', 1))
+        self.rank = int(os.environ.get('RANK', 0))
+        self.local = int(os.environ.get('LOCAL_RANK', 0))
+        if not torch.cuda.is_available():
+            raise RuntimeError('bench.py needs a CUDA device; there is no CPU path')
+        torch.cuda.set_device(self.local)
+        if self.world > 1:
+            td.init_process_group('nccl', device_id=torch.device('cuda', self.local))
+
+    def barrier(self):
+        if self.world > 1:
+            self.td.barrier()
+        self.torch.cuda.synchronize()
+
+    def timed_loop(self, fn, steps):
+        """K steps between barrier + synchronize on both sides, CUDA events on
+        the current stream, maximum over the ranks."""
+        torch = self.torch
+        self.barrier()
+        e0 = torch.cuda.Event(enable_timing=True)
+        e1 = torch.cuda.Event(enable_timing=True)
+        e0.record()
+        out = None
+        for _ in range(steps):
+            out = fn()
+        e1.record()
+        self.barrier()
+        ms = e0.elapsed_time(e1)
+        return self.max_over_ranks(ms), out
+
+    def max_over_ranks(self, x):
+        if self.world > 1:
+            t = self.torch.tensor([float(x)], device='cuda', dtype=self.torch.float64)
+            self.td.all_reduce(t, op=self.td.ReduceOp.MAX)
+            return float(t.item())
+        return float(x)
+
+    def sum_over_ranks(self, x):
+        if self.world > 1:
+            t = self.torch.tensor([float(x)], device='cuda', dtype=self.torch.float64)
+            self.td.all_reduce(t, op=self.td.ReduceOp.SUM)
+            return float(t.item())
+        return float(x)
+
+    def gather_list(self, x):
+        if self.world > 1:
+            parts = [None] * self.world
+            self.td.all_gather_object(parts, x)
+            return parts
+        return [x]
+
+    def close(self):
+        if self.world > 1:
+            self.td.destroy_process_group()
+
+
+def station_oracle(dims, stations, method='median', prob=0.95):
+    """The oracle's detect() for the benchmark's stations, from their columns
+    only: station s becomes node (s+1, 1) of an [S x 1 x dz] mini grid whose
+    columns are regenerated from the seed (the full 16 GB stack is never built
+    on the host).  Returns (flags [S][dz], detected [S])."""
     import pandas as pd
+    from gsimcli_b200 import synth
+    from oracle import np_oracle as O
+    S, dz = len(stations), dims[2]
+    per = dims[0] * dims[1]
+    mini = np.empty((R, S * dz), dtype=np.float32)
+    for s, stn in enumerate(stations):
+        x = int(round((stn['obs'][0][0] - FIRST[0]) / CELLS[0])) + 1
+        y = int(round((stn['obs'][0][1] - FIRST[1]) / CELLS[1])) + 1
+        nodes = (x - 1) + dims[0] * (y - 1) + per * np.arange(dz)
+        mini[:, s + S * np.arange(dz)] = synth.columns(SEED, R, dims, nodes, ND)
+    flags = np.empty((S, dz))
+    det = np.empty(S, dtype=np.int64)
+    for s, stn in enumerate(stations):
+        df = pd.DataFrame(stn['obs'], columns=OCOLS)
+        df['x'], df['y'] = float(s), 0.0
+        hom, dn, _ = O.detect(mini, [S, 1, dz], [0.0, 0.0, FIRST[2]], [1.0, 1.0, CELLS[2]],
+                              ND, df, ND, method=method, prob=prob)
+        flags[s] = hom['Flag'].values
+        det[s] = dn
+    return flags, det
+
+
+# ------------------------------------------------------------------ config 3
+def run_cfg3(args):
     import torch
-    import torch.distributed as td
     from gsimcli_b200 import _capi, synth, dist
     from gsimcli_b200.tools import grid as gr, homog as hmg
-
-    world = int(os.environ.get('WORLD_SIZE', 1))
-    rank = int(os.environ.get('RANK', 0))
-    local = int(os.environ.get('LOCAL_RANK', 0))
-    if not torch.cuda.is_available():
-        raise RuntimeError('bench.py needs a CUDA device; there is no CPU path')
-    torch.cuda.set_device(local)
-    if world > 1:
-        td.init_process_group('nccl', device_id=torch.device('cuda', local))
-
-    dims = [DIMS1[0], DIMS1[1], DIMS1[2] * world]
+    D = Dist()
+    world, rank, local = D.world, D.rank, D.local
+    strong = args.scaling == 'strong'
+    dims = list(DIMS1) if strong else [DIMS1[0], DIMS1[1], DIMS1[2] * world]
+    ntotal = int(np.prod(dims))
     n0, n1 = dist.slab_range(dims, rank, world)
     nn = n1 - n0
-    grids = gr.GridFiles.from_synthetic(SEED, R, dims, FIRST, CELLS, ND,
-                                        device=local,
+    grids = gr.GridFiles.from_synthetic(SEED, R, dims, FIRST, CELLS, ND, device=local,
                                         node_range=(n0, n1) if world > 1 else None)
     stack = grids._stack
     flags = (_capi.MEAN | _capi.MEDIAN | _capi.SKEW | _capi.VAR | _capi.STD
@@ -216,16 +350,17 @@ def run_gpu(args):
     out_pitch = (nn + 3) // 4 * 4
     d_out = torch.empty((nplanes, out_pitch), dtype=torch.float32, device='cuda')
     stations = synth.stations(SEED, NSTATIONS, R, dims, FIRST, CELLS)
-    cols = ['x', 'y', 'time', 'station', 'clim']
 
     def obs_list():
-        return [gr.PointSet('cand%d' % i, ND, 5, list(cols),
+        return [gr.PointSet('cand%d' % i, ND, 5, list(OCOLS),
                             np.array(s['obs'], dtype=np.float64))
                 for i, s in enumerate(stations)]
 
+    # the station path is prepared once (host glue: point-set clean-up, node
+    # ids) and then lives on the device: K2c -> all-gather -> K3 -> one D2H
+    plan = hmg.DetectPlan(grids, obs_list(), method='median', prob=0.95)
     # K2 runs on its own stream and leaves a few SMs free; the station path
-    # (K2c + K3, tiny) runs on a second stream concurrently with it, so its
-    # host-side pandas glue overlaps the full-grid kernel
+    # (tiny) runs on a second stream concurrently with it
     stack.set_option('k2_sm_reserve', int(os.environ.get('GSB_K2_RESERVE', 4)))
     s_grid = torch.cuda.Stream()
     s_stat = torch.cuda.Stream()
@@ -244,109 +379,119 @@ def run_gpu(args):
                                 out_pitch, s_grid.cuda_stream)
         if timed:
             ev_k1.record(s_grid)
-        res = hmg.detect_many(grids, obs_list(), method='median', prob=0.95,
-                              stream=s_stat.cuda_stream)
+        plan.enqueue(s_stat)
         cur.wait_stream(s_grid)
         cur.wait_stream(s_stat)
+        res = plan.fetch()                   # station results on the host
         if timed:
             ev_k1.synchronize()
             kernel_ms.append(ev_k0.elapsed_time(ev_k1))
         return res
 
-    def barrier():
-        if world > 1:
-            td.barrier()
-        torch.cuda.synchronize()
-
-    def timed_loop(fn, steps):
-        barrier()
-        e0 = torch.cuda.Event(enable_timing=True)
-        e1 = torch.cuda.Event(enable_timing=True)
-        e0.record()
-        for _ in range(steps):
-            out = fn()
-        e1.record()
-        barrier()
-        ms = e0.elapsed_time(e1)
-        if world > 1:
-            t = torch.tensor([ms], device='cuda')
-            td.all_reduce(t, op=td.ReduceOp.MAX)
-            ms = float(t.item())
-        return ms, out
-
     sampler = ClockSampler(local)
     for _ in range(args.warmup):
         step_resident(False)
     sampler.start()
-    ms_total, res = timed_loop(lambda: step_resident(True), args.steps)
-    units_per_step = float(R) * nn * world
+    ms_total, res = D.timed_loop(lambda: step_resident(True), args.steps)
+    units_per_step = float(R) * ntotal
     value = units_per_step * args.steps / (ms_total * 1e-3)
-    detected = int(sum(r[1] for r in res))
+    flag_gpu = np.array(res[2], copy=True)
+    det_gpu = np.array(res[3], copy=True)
+    detected = int(det_gpu.sum())
+
+    # ---- parity of this very run against the oracle
+    parity = {}
+    oflags, odet = station_oracle(dims, stations)
+    st_bad = int((flag_gpu != oflags).sum()) + int((det_gpu != odet).sum())
+    parity['stations'] = {'stations': NSTATIONS, 'time_steps': dims[2],
+                          'flag_mismatches': st_bad,
+                          'flags_crc32': int(zlib.crc32(flag_gpu.tobytes()))}
+    crcs = D.gather_list(parity['stations']['flags_crc32'])
+    parity['stations']['identical_on_all_ranks'] = len(set(crcs)) == 1
+    fast = bool(os.environ.get('GSB_BENCH_FAST'))   # developer runs: short CPU legs
+    cpu_val = cpu_wall = None
+    cpu_nodes = 4096 if fast else int(os.environ.get('GSB_CPU_NODES', 262144))
+    if rank == 0:
+        # the CPU baseline sample doubles as the full-grid parity sample: columns
+        # of this rank's slab, oracle planes against the maps the GPU just wrote
+        nodes = sample_nodes(dims, cpu_nodes, n0, n1)
+        cpu_val, cpu_wall, ref = cpu_sample(dims, nodes, 1, keep=True)
+        got = d_out[:, torch.from_numpy(nodes - n0).cuda()].cpu().numpy().astype(np.float64)
+        exact = [1] + list(range(6, nplanes))              # median, percentiles, mode
+        g32 = got[exact].astype(np.float32)
+        r32 = ref[exact].astype(np.float32)
+        bad = int((~((g32 == r32) | (np.isnan(g32) & np.isnan(r32)))).sum())
+        with np.errstate(all='ignore'):
+            rel = np.abs(got[[0, 3, 4, 5]] - ref[[0, 3, 4, 5]]) / np.abs(ref[[0, 3, 4, 5]])
+            skew_abs = np.abs(got[2] - ref[2])
+            skew_ok = skew_abs <= 1e-5 + 1e-5 * np.abs(ref[2])
+        parity['grid'] = {'columns': int(len(nodes)), 'order_stat_mismatches': bad,
+                          'max_rel_moment': float(np.nanmax(rel)),
+                          'max_abs_skew_err': float(np.nanmax(skew_abs)),
+                          'moment_mismatches': int((rel > 1e-5).sum() + (~skew_ok).sum())}
+        if bad or parity['grid']['moment_mismatches'] or st_bad or \
+                not parity['stations']['identical_on_all_ranks']:
+            raise RuntimeError('PARITY FAILURE: {0}'.format(json.dumps(parity)))
 
     # ---- e2e: the float32 stack in pinned host memory, maps back to host
     e2e = None
-    fast = bool(os.environ.get('GSB_BENCH_FAST'))   # developer runs: resident leg only
     try:
-        if fast:
+        if fast and world == 1:
             raise RuntimeError('skipped (GSB_BENCH_FAST)')
         pitch = stack.pitch
         host = torch.empty((R, pitch), dtype=torch.float32, pin_memory=True)
-        dview = torch.empty(0)
         import ctypes
         # one-off D2H of the resident synthetic stack (setup, not timed)
         _capi.check(_capi.lib().gsb_stack_download_f32(
-            stack.handle, 0, R, 0, nn, ctypes.c_void_p(host.data_ptr()), pitch,
-            None))
-        del dview
+            stack.handle, 0, R, 0, nn, ctypes.c_void_p(host.data_ptr()), pitch, None))
         maps = torch.empty((nplanes, nn), dtype=torch.float32, pin_memory=True)
-        maps_np = maps.numpy()
-
-        stream = torch.cuda.current_stream().cuda_stream
 
         def step_e2e():
             # upload, reduction and map download pipelined over node slabs
             stack.stats_grid_from_host(host.data_ptr(), pitch, flags, 0.95, QS,
                                        ND, maps)
-            res = hmg.detect_many(grids, obs_list(), method='median',
-                                  prob=0.95, stream=stream)
+            plan.enqueue(torch.cuda.current_stream())
+            r2 = plan.fetch()
             torch.cuda.current_stream().synchronize()      # maps are on the host
-            return res
+            return r2
 
         e2e_steps = max(1, min(args.steps, 3))
         step_e2e()
-        ms_e2e, res2 = timed_loop(step_e2e, e2e_steps)
-        assert int(sum(r[1] for r in res2)) == detected
+        t0 = time.perf_counter()
+        ms_e2e, res2 = D.timed_loop(step_e2e, e2e_steps)
+        assert int(np.sum(res2[3])) == detected
         # the pipelined host path must reproduce the resident maps bit for bit
         same = (maps.to('cuda').view(torch.int32) == d_out[:, :nn].view(torch.int32))
         assert bool(same.all()), 'e2e maps differ from the resident-stack maps'
         del same
+        h2d = float(R) * nn * 4
+        per_rank = D.gather_list(h2d * e2e_steps / (ms_e2e * 1e-3) / 1e9)
         e2e = {'value': units_per_step * e2e_steps / (ms_e2e * 1e-3),
-               'unit': UNIT, 'h2d_bytes_per_step': int(R * nn * 4 * world),
-               'd2h_bytes_per_step': int(nplanes * nn * 4 * world),
+               'unit': UNIT, 'h2d_bytes_per_step': int(D.sum_over_ranks(h2d)),
+               'd2h_bytes_per_step': int(D.sum_over_ranks(nplanes * nn * 4 + 3 * NSTATIONS * dims[2] * 8)),
                'steps': e2e_steps, 'ms_per_step': ms_e2e / e2e_steps,
-               'input': 'float32 stack in pinned host memory, uploaded in 8 node '
-                        'slabs overlapped with K2 and the map download'}
+               'h2d_gbs_per_rank': [round(x, 2) for x in per_rank],
+               'input': 'float32 stack in pinned host memory, each rank uploads its own '
+                        'slab in 8 node pieces overlapped with K2 and the map download'}
         del host, maps
     except (RuntimeError, MemoryError) as exc:     # e.g. cannot pin 16 GB
         e2e = {'value': None, 'unit': UNIT, 'error': str(exc)[:200]}
-    sampler.stop_flag.set()
-    sampler.join(timeout=2)
+    clocks = sampler.finish()
 
+    kms = D.gather_list(float(np.mean(kernel_ms)))
     if rank == 0:
         peak, peak_src = peaks()
         k_ms = float(np.mean(kernel_ms))
         alg_bytes = 4.0 * R * nn + 4.0 * nplanes * nn
         achieved = alg_bytes / (k_ms * 1e-3) / 1e9
         cores = len(os.sched_getaffinity(0))
-        cpu_nodes = int(os.environ.get('GSB_CPU_NODES', 262144))
-        cpu_val, cpu_wall = cpu_sample(dims, 4096 if fast else cpu_nodes, 1)
         line = {
             'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world,
             'steps': args.steps, 'warmup': args.warmup,
             'ms_per_step': ms_total / args.steps, 'higher_is_better': True,
-            'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32',
+            'scaling': args.scaling, 'vs_baseline': None, 'dtype': 'f32',
             'data': 'synthetic',
-            'config': {'workload': workload_name(world),
+            'config': {'workload': workload_name(world, args.scaling, 3),
                        'l2': 'inputs larger than L2 ({0:.1f} GB stack per GPU)'
                        .format(R * nn * 4 / 1e9),
                        'detected': detected},
@@ -356,20 +501,243 @@ def run_gpu(args):
                          'unit': 'GB/s', 'frac': achieved / peak,
                          'frac_of_nominal_8TBs': achieved / 8000.0,
                          'traffic': measured_traffic(R, nn), 'kernel': 'k2_csort_kernel',
-                         'kernel_ms': k_ms, 'algorithmic_bytes': alg_bytes,
-                         'peak_source': peak_src},
+                         'kernel_ms': k_ms, 'kernel_ms_per_rank': [round(x, 3) for x in kms],
+                         'algorithmic_bytes': alg_bytes, 'peak_source': peak_src},
             'cpu_baseline': {
                 'value': cpu_val, 'unit': UNIT, 'cores': 1, 'kind': 'port',
                 'host_cores_available': cores,
                 'sample': ('{0} node columns x {1} realizations, NumPy oracle '
                            '(oracle/np_oracle.py), {2:.1f} s').format(
                                cpu_nodes, R, cpu_wall)},
-            'clocks': sampler.summary(),
+            'parity': parity,
+            'clocks': clocks,
         }
         print(json.dumps(line))
     grids.dump()
-    if world > 1:
-        td.destroy_process_group()
+    D.close()
+
+
+# ------------------------------------------------------------------ config 4
+C4_FILES = int(os.environ.get('GSB_C4_FILES', 500))
+C4_WIDTH = 14            # '%12.4f\r\n' (interface/gui.py:1414)
+
+
+def run_cfg4(args):
+    """Realization TEXT in pinned host memory -> K1 decode -> K2 statistics.
+    Each rank holds the byte range of its own nodes of every file (O(1)
+    offsets: 14 bytes per node).  The text is produced on the device by the
+    encoder (inverse of K1) from the synthetic stack and copied to the host
+    during set-up; that is not timed."""
+    import torch
+    from gsimcli_b200 import _capi, dist
+    from gsimcli_b200.tools import grid as gr
+    D = Dist()
+    world, rank, local = D.world, D.rank, D.local
+    dims = list(DIMS1)
+    ntotal = int(np.prod(dims))
+    n0, n1 = dist.slab_range(dims, rank, world)
+    nn = n1 - n0
+    RF = C4_FILES
+    L = _capi.lib()
+    src = gr.GridFiles.from_synthetic(SEED, RF, dims, FIRST, CELLS, ND, device=local,
+                                      node_range=(n0, n1) if world > 1 else None)
+    nbytes = nn * C4_WIDTH
+    dtext = torch.empty(nbytes + 64, dtype=torch.uint8, device='cuda')
+    texts = []
+    for r in range(RF):
+        _capi.check(L.gsb_encode_text_device(src._stack.handle, r, 0, nn, 12, 4, 1,
+                                             dtext.data_ptr(), None))
+        t = torch.empty(nbytes, dtype=torch.uint8, pin_memory=True)
+        t.copy_(dtext[:nbytes])
+        texts.append(t)
+    torch.cuda.synchronize()
+    flags = _capi.MEAN | _capi.MEDIAN | _capi.SKEW | _capi.PERC
+    nplanes = L.gsb_stats_grid_planes(flags, 0)
+    ref_maps = torch.empty((nplanes, nn), dtype=torch.float32, device='cuda')
+    src._stack.stats_grid_device(flags, 0.95, None, ND, 0, nn, ref_maps.data_ptr(), nn, None)
+    torch.cuda.synchronize()
+    src.dump()
+    maps = torch.empty((nplanes, nn), dtype=torch.float32, pin_memory=True)
+    d_maps = torch.empty((nplanes, nn), dtype=torch.float32, device='cuda')
+    k_ms = []
+
+    def step(keep=False):
+        g = gr.GridFiles.from_pinned_text(texts, dims, FIRST, CELLS, ND, C4_WIDTH,
+                                          device=local,
+                                          node_range=(n0, n1) if world > 1 else None)
+        e0 = torch.cuda.Event(enable_timing=True)
+        e1 = torch.cuda.Event(enable_timing=True)
+        e0.record()
+        g._stack.stats_grid_device(flags, 0.95, None, ND, 0, nn, d_maps.data_ptr(), nn, None)
+        e1.record()
+        maps.copy_(d_maps, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        k_ms.append(e0.elapsed_time(e1))
+        if keep:
+            return g
+        g.dump()
+        return None
+
+    sampler = ClockSampler(local)
+    for _ in range(max(1, min(args.warmup, 2))):
+        step()
+    sampler.start()
+    steps = max(1, min(args.steps, 3))
+    ms_total, _ = D.timed_loop(step, steps)
+    same = (maps.to('cuda').view(torch.int32) == ref_maps.view(torch.int32)) | \
+        (torch.isnan(maps.to('cuda')) & torch.isnan(ref_maps))
+    ok = bool(same.all())
+    # resident decode rate: the text of one file already in HBM
+    g = step(keep=True)
+    dtext[:nbytes].copy_(texts[0])
+    bad = torch.full((1,), -1, dtype=torch.int64, device='cuda')
+    torch.cuda.synchronize()
+    e0 = torch.cuda.Event(enable_timing=True)
+    e1 = torch.cuda.Event(enable_timing=True)
+    e0.record()
+    reps = 20
+    for _ in range(reps):
+        _capi.check(L.gsb_decode_text_device(g._stack.handle, 0, dtext.data_ptr(), nbytes, 0,
+                                             C4_WIDTH, 0, 0, nn, bad.data_ptr(), None))
+    e1.record()
+    torch.cuda.synchronize()
+    k1_ms = e0.elapsed_time(e1) / reps
+    g.dump()
+    clocks = sampler.finish()
+    units = float(RF) * ntotal
+    text_bytes = float(RF) * nn * C4_WIDTH
+    gbs_rank = D.gather_list(text_bytes * steps / (ms_total * 1e-3) / 1e9)
+    if not ok:
+        raise RuntimeError('PARITY FAILURE: maps from decoded text differ from the '
+                           'maps of the stack the text was printed from')
+    if rank == 0:
+        peak, peak_src = peaks()
+        k1_alg = (C4_WIDTH + 4.0) * nn
+        line = {
+            'metric': METRIC, 'value': units * steps / (ms_total * 1e-3), 'unit': UNIT,
+            'n_gpus': world, 'steps': steps, 'warmup': max(1, min(args.warmup, 2)),
+            'ms_per_step': ms_total / steps, 'higher_is_better': True,
+            'scaling': 'strong', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+            'config': {'workload': workload_name(world, 'strong', 4),
+                       'l2': 'inputs larger than L2',
+                       'statistics': 'mean, median, skewness, percentile pair (the '
+                                     'reference call, grid.py:601-602)'},
+            'e2e': {'value': units * steps / (ms_total * 1e-3), 'unit': UNIT,
+                    'h2d_bytes_per_step': int(D.sum_over_ranks(text_bytes)),
+                    'd2h_bytes_per_step': int(D.sum_over_ranks(nplanes * nn * 4)),
+                    'text_gbs_per_rank': [round(x, 2) for x in gbs_rank],
+                    'input': 'text in pinned host memory; H2D, K1 decode (3 streams) and '
+                             'K2 inside the timed region'},
+            'gpu_launches': (RF + 1) * steps,
+            'roofline': {'bound': 'hbm', 'kernel': 'k1_decode (fixed width, text resident in HBM)',
+                         'achieved': k1_alg / (k1_ms * 1e-3) / 1e9, 'peak': peak, 'unit': 'GB/s',
+                         'frac': k1_alg / (k1_ms * 1e-3) / 1e9 / peak, 'kernel_ms': k1_ms,
+                         'algorithmic_bytes': k1_alg, 'traffic': None, 'peak_source': peak_src,
+                         'k2_kernel_ms': float(np.mean(k_ms))},
+            'parity': {'maps_from_text_equal_maps_from_stack': ok, 'planes': nplanes,
+                       'nodes': int(D.sum_over_ranks(nn))},
+            'clocks': clocks,
+        }
+        print(json.dumps(line))
+    D.close()
+
+
+# ------------------------------------------------------------------ config 5
+C5_NETWORKS = int(os.environ.get('GSB_C5_NETWORKS', 100))
+C5_R = 100
+C5_DIMS = [80, 80, 50]
+C5_STATIONS = 10
+C5_PROBS = [0.90, 0.925, 0.95, 0.975, 0.99]
+
+
+def run_cfg5(args):
+    """Batch homogenisation: whole networks round-robin over the ranks
+    (replicas, no data-path collective); per network the stack is filled, its
+    local-PDF maps are reduced (the reference call) and every candidate is
+    tested at five detection probabilities from ONE reduction of the station
+    columns (detect_sweep)."""
+    import pandas as pd
+    import torch
+    from gsimcli_b200 import _capi, synth
+    from gsimcli_b200.tools import grid as gr, homog as hmg
+    from oracle import np_oracle as O
+    D = Dist()
+    world, rank, local = D.world, D.rank, D.local
+    dims, first, cells = C5_DIMS, [0.0, 0.0, 1950], [500.0, 500.0, 1]
+    nn = int(np.prod(dims))
+    flags = _capi.MEAN | _capi.MEDIAN | _capi.SKEW | _capi.PERC
+    nplanes = _capi.lib().gsb_stats_grid_planes(flags, 0)
+    d_maps = torch.empty((nplanes, nn), dtype=torch.float32, device='cuda')
+    mine = [i for i in range(C5_NETWORKS) if i % world == rank]
+    sts = {i: synth.stations(7000 + i, C5_STATIONS, C5_R, dims, first, cells) for i in mine}
+
+    def obs(i):
+        return [gr.PointSet('n%dc%d' % (i, k), ND, 5, list(OCOLS),
+                            np.array(s['obs'], dtype=np.float64))
+                for k, s in enumerate(sts[i])]
+
+    def step():
+        out = {}
+        for i in mine:
+            g = gr.GridFiles.from_synthetic(7000 + i, C5_R, dims, first, cells, ND,
+                                            device=local)
+            g._stack.stats_grid_device(flags, 0.95, None, ND, 0, nn, d_maps.data_ptr(),
+                                       nn, None)
+            sweep = hmg.detect_sweep(g, obs(i), C5_PROBS, method='median')
+            out[i] = {p: [(dn, md) for (_, dn, md) in sweep[p]] for p in C5_PROBS}
+            out[i]['flags'] = {p: [np.array(h.values['Flag'].values) for (h, _, _) in sweep[p]]
+                               for p in C5_PROBS}
+            g.dump()
+        torch.cuda.synchronize()
+        return out
+
+    sampler = ClockSampler(local)
+    for _ in range(max(1, min(args.warmup, 1))):
+        step()
+    sampler.start()
+    steps = max(1, min(args.steps, 3))
+    ms_total, out = D.timed_loop(step, steps)
+    clocks = sampler.finish()
+    # parity: every (network, probability, station) of the first networks of
+    # this rank against the oracle
+    checked = bad = 0
+    for i in mine[:int(os.environ.get('GSB_C5_CHECK', 2))]:
+        host = synth.stack(7000 + i, C5_R, dims)
+        for p in C5_PROBS:
+            for k, s in enumerate(sts[i]):
+                df = pd.DataFrame(s['obs'], columns=OCOLS)
+                ohom, odn, omd = O.detect(host, dims, first, cells, ND, df, ND,
+                                          method='median', prob=p)
+                checked += 1
+                if (odn, omd) != out[i][p][k] or not np.array_equal(
+                        out[i]['flags'][p][k], ohom['Flag'].values):
+                    bad += 1
+    bad = int(D.sum_over_ranks(bad))
+    checked = int(D.sum_over_ranks(checked))
+    if bad:
+        raise RuntimeError('PARITY FAILURE: {0} of {1} (network, prob, station) results '
+                           'differ from the oracle'.format(bad, checked))
+    if rank == 0:
+        units = float(C5_NETWORKS) * C5_R * nn
+        line = {
+            'metric': METRIC, 'value': units * steps / (ms_total * 1e-3), 'unit': UNIT,
+            'n_gpus': world, 'steps': steps, 'warmup': 1, 'ms_per_step': ms_total / steps,
+            'higher_is_better': True, 'scaling': 'strong', 'vs_baseline': None,
+            'dtype': 'f32', 'data': 'synthetic',
+            'config': {'workload': workload_name(world, 'strong', 5),
+                       'l2': '128 MB stack per network, regenerated every step'},
+            'e2e': {'value': units * steps / (ms_total * 1e-3), 'unit': UNIT,
+                    'h2d_bytes_per_step': 0,
+                    'd2h_bytes_per_step': int(C5_NETWORKS * C5_STATIONS * dims[2] * 8 * 3
+                                              * len(C5_PROBS)),
+                    'input': 'stacks generated on the device (DSS output is not part of '
+                             'the path); station results per probability on the host'},
+            'gpu_launches': C5_NETWORKS * (3 + len(C5_PROBS)) * steps,
+            'parity': {'results_checked': checked, 'mismatches': bad},
+            'clocks': clocks,
+        }
+        print(json.dumps(line))
+    D.close()
 
 
 def main():
@@ -378,11 +746,17 @@ def main():
     ap.add_argument('--steps', type=int, default=10)
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='b200')
+    ap.add_argument('--config', type=int, default=3, choices=[3, 4, 5])
+    ap.add_argument('--scaling', default='strong', choices=['strong', 'weak'])
     args = ap.parse_args()
     if args.impl == 'reference':
         run_reference(args)
+    elif args.config == 4:
+        run_cfg4(args)
+    elif args.config == 5:
+        run_cfg5(args)
     else:
-        run_gpu(args)
+        run_cfg3(args)
 
 
 if __name__ == '__main__':

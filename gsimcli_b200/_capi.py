@@ -52,6 +52,8 @@ SIGNATURES = {
     'gsb_stack_device_ptr': (C.c_int, [c_vp, C.POINTER(c_vp)]),
     'gsb_stack_upload_f32': (C.c_int, [c_vp, c_i64, c_i64, c_i64, c_i64, c_vp,
                                        c_i64, c_vp]),
+    'gsb_stack_upload_f32_async': (C.c_int, [c_vp, c_i64, c_i64, c_i64, c_i64,
+                                             c_vp, c_i64, c_vp]),
     'gsb_stack_download_f32': (C.c_int, [c_vp, c_i64, c_i64, c_i64, c_i64,
                                          c_vp, c_i64, c_vp]),
     'gsb_decode_text': (C.c_int, [c_vp, c_i64, c_vp, C.c_size_t, C.c_int,
@@ -70,6 +72,11 @@ SIGNATURES = {
     'gsb_stats_columns': (C.c_int, [c_vp, p_i64, C.c_int, C.c_int, C.c_int,
                                     C.c_uint32, C.c_double, p_f64, C.c_int,
                                     C.c_float, c_vp, C.c_int, c_vp]),
+    'gsb_stats_columns_device': (C.c_int, [c_vp, c_vp, C.c_int, C.c_int, C.c_int,
+                                          C.c_uint32, C.c_double, p_f64, C.c_int,
+                                          C.c_float, c_vp, c_vp]),
+    'gsb_detect_table': (C.c_int, [c_vp, c_vp, c_vp, c_vp, c_i64] + [C.c_int] * 11
+                         + [C.c_double, C.c_double, c_vp, c_vp, C.c_int, c_vp]),
     'gsb_extract_columns': (C.c_int, [c_vp, p_i64, C.c_int, C.c_int, C.c_int,
                                       c_vp, c_vp]),
     'gsb_detect': (C.c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, C.c_int,
@@ -276,7 +283,7 @@ class Stack(object):
         step = (step + 31) // 32 * 32             # whole 32-node tiles per slab
         for a in range(0, self.N, step):
             b = min(self.N, a + step)
-            check(lib().gsb_stack_upload_f32(
+            check(lib().gsb_stack_upload_f32_async(
                 self.handle, 0, self.R, a, b - a, c_vp(host_ptr + 4 * a),
                 host_pitch, c_vp(up.cuda_stream)))
             ev = torch.cuda.Event()
@@ -316,6 +323,27 @@ class Stack(object):
         check(lib().gsb_extract_columns(self.handle, ids.ctypes.data_as(p_i64),
                                         S, dz, K, _ptr(vals), stream))
         return vals
+
+
+def encode_values(values, width, prec, crlf=False, left=False, device=0):
+    """Fixed-width text records of a float32 vector, formatted on the device
+    (``gsb_encode_text_device``): uint8 array ``[n][width + eol]``."""
+    import torch
+    vals = np.ascontiguousarray(values, dtype=np.float32).reshape(1, -1)
+    n = vals.shape[1]
+    rec = width + (2 if crlf else 1)
+    stack = Stack(1, n, device)
+    try:
+        stack.upload(vals)
+        dtext = torch.empty(n * rec, dtype=torch.uint8,
+                            device=torch.device('cuda', device))
+        check(lib().gsb_encode_text_device(
+            stack.handle, 0, 0, n, width, prec, (1 if crlf else 0) | (2 if left else 0),
+            dtext.data_ptr(), None))
+        out = dtext.cpu().numpy().reshape(n, rec)
+    finally:
+        stack.close()
+    return out
 
 
 def detect(clim, mean, lperc, rperc, fix_a, fix_b=None, fix_c=None,

@@ -258,8 +258,8 @@ static int check_range(const gsb_stack* s, int64_t r0, int64_t nr, int64_t n0, i
     return GSB_OK;
 }
 
-int gsb_stack_upload_f32(gsb_stack* s, int64_t r0, int64_t nr, int64_t n0, int64_t nn,
-                         const float* host, int64_t host_pitch, void* stream) {
+int gsb_stack_upload_f32_async(gsb_stack* s, int64_t r0, int64_t nr, int64_t n0, int64_t nn,
+                               const float* host, int64_t host_pitch, void* stream) {
     int rc = check_range(s, r0, nr, n0, nn);
     if (rc) return rc;
     GSB_REQUIRE(host && host_pitch >= nn, "bad host buffer");
@@ -269,7 +269,15 @@ int gsb_stack_upload_f32(gsb_stack* s, int64_t r0, int64_t nr, int64_t n0, int64
     GSB_CUDA(cudaMemcpy2DAsync(s->data + r0 * s->pitch + n0, (size_t)s->pitch * 4, host,
                                (size_t)host_pitch * 4, (size_t)nn * 4, (size_t)nr,
                                cudaMemcpyHostToDevice, st));
-    GSB_CUDA(cudaStreamSynchronize(st));
+    return GSB_OK;
+}
+
+int gsb_stack_upload_f32(gsb_stack* s, int64_t r0, int64_t nr, int64_t n0, int64_t nn,
+                         const float* host, int64_t host_pitch, void* stream) {
+    int rc = gsb_stack_upload_f32_async(s, r0, nr, n0, nn, host, host_pitch, stream);
+    if (rc) return rc;
+    if (nr == 0 || nn == 0) return GSB_OK;
+    GSB_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
     return GSB_OK;
 }
 
@@ -460,6 +468,40 @@ int gsb_stats_columns(gsb_stack* s, const int64_t* node_ids, int S, int dz, int 
         GSB_CUDA(cudaStreamSynchronize(st));
     }
     return GSB_OK;
+}
+
+int gsb_stats_columns_device(gsb_stack* s, const int64_t* d_node_ids, int S, int dz, int K,
+                             uint32_t flags, double p, const double* q, int nq, float nodata,
+                             double* d_table, void* stream) {
+    GSB_REQUIRE(s && d_node_ids && d_table, "NULL argument");
+    GSB_REQUIRE(S >= 0 && dz >= 0 && K >= 1, "bad S/dz/K");
+    GSB_REQUIRE(nq >= 0 && (nq == 0 || q), "bad quantile list");
+    GsbPlanes pl;
+    int rc = gsb_build_planes(flags, p, q, nq, &pl);
+    if (rc) return rc;
+    if ((int64_t)S * dz == 0 || pl.n == 0) return GSB_OK;
+    GSB_CUDA(cudaSetDevice(s->device));
+    return gsb_launch_k2_columns(s, d_node_ids, S, dz, K, pl, nodata, d_table, (cudaStream_t)stream);
+}
+
+int gsb_detect_table(const double* d_clim, const double* d_table, const double* d_fixtab,
+                     const int64_t* d_zoff, int64_t sstride, int C, int Cfix, int c_mean,
+                     int c_lperc, int c_rperc, int c_fa, int c_fb, int c_fc, int S, int dz,
+                     int method, double thr, double nodata, double* d_out, int32_t* d_detected,
+                     int device, void* stream) {
+    GSB_REQUIRE(d_clim && d_table && d_fixtab && d_zoff && d_out && d_detected, "NULL argument");
+    GSB_REQUIRE(method >= GSB_METHOD_MEAN && method <= GSB_METHOD_PERCENTILE,
+                "Method %d invalid or incomplete.", method);
+    GSB_REQUIRE(S >= 0 && dz >= 0 && C >= 1 && Cfix >= 1, "bad S/dz/C");
+    GSB_REQUIRE(c_mean >= 0 && c_mean < C && c_lperc >= 0 && c_lperc < C && c_rperc >= 0 &&
+                c_rperc < C && c_fa >= 0 && c_fa < Cfix && c_fb >= 0 && c_fb < Cfix && c_fc < C,
+                "column index outside the table");
+    GSB_REQUIRE(method != GSB_METHOD_SKEWNESS || c_fc >= 0, "skewness method needs the skewness column");
+    if (S == 0 || dz == 0) return GSB_OK;
+    GSB_CUDA(cudaSetDevice(device));
+    return gsb_launch_k3_detect_table(d_clim, d_table, d_fixtab, d_zoff, sstride, C, Cfix, c_mean,
+                                      c_lperc, c_rperc, c_fa, c_fb, c_fc, S, dz, method, thr,
+                                      nodata, d_out, d_detected, (cudaStream_t)stream);
 }
 
 int gsb_extract_columns(gsb_stack* s, const int64_t* node_ids, int S, int dz, int K,

@@ -113,6 +113,11 @@ int gsb_launch_k3_detect(const double* clim, const double* mean,
                          double thr, double nodata, double* filled,
                          double* homog, double* flag, int32_t* detected,
                          cudaStream_t st);
+int gsb_launch_k3_detect_table(const double* clim, const double* table, const double* fixtab,
+                               const int64_t* zoff, int64_t sstride, int C, int Cfix, int c_mean,
+                               int c_lperc, int c_rperc, int c_fa, int c_fb, int c_fc, int S, int dz,
+                               int method, double thr, double nodata, double* out,
+                               int32_t* detected, cudaStream_t st);
 int gsb_launch_synth(gsb_stack* s, uint64_t seed, int64_t dx, int64_t dy,
                      int64_t dz, int64_t node0, float nodata, cudaStream_t st);
 int gsb_launch_decode(gsb_stack* s, int64_t r, const char* dtext, size_t nbytes,

@@ -413,31 +413,42 @@ k1_decode_general(const char* __restrict__ text, long long nbytes,
 // fixed-width '%<width>.<prec>f' + EOL, correctly rounded for values whose
 // scaled magnitude fits 2^53 (all GSLIB-style data); one thread per value
 __global__ void __launch_bounds__(K1_THREADS)
-k1_encode_fixed(const float* __restrict__ row, long long nn, int width, int prec, int crlf,
+k1_encode_fixed(const float* __restrict__ row, long long nn, int width, int prec, int eolmode,
                 char* __restrict__ text) {
     const long long i = static_cast<long long>(blockIdx.x) * K1_THREADS + threadIdx.x;
     if (i >= nn) return;
+    const bool crlf = (eolmode & 1) != 0, left = (eolmode & 2) != 0;
     const int W = width + (crlf ? 2 : 1);
     char* p = text + i * W;
     const double v = static_cast<double>(row[i]);
-    const bool negv = v < 0;
+    const bool negv = __double_as_longlong(v) < 0;       // sign bit: printf prints -0.000000
     const double av = fabs(v);
-    double scale = 1.0;
-    for (int k = 0; k < prec; ++k) scale *= 10.0;
-    // exact decimal expansion of a binary float is finite: round-half-even on
-    // the exact product (av*scale is exact when it fits 53 bits; the synthetic
-    // lattice values and 6-decimal maps do)
-    const double scaled = av * scale;
-    unsigned long long q = static_cast<unsigned long long>(rint(scaled));
     char tmp[40];
     int n = 0;
-    for (int k = 0; k < prec; ++k) { tmp[n++] = '0' + static_cast<int>(q % 10); q /= 10; }
-    if (prec > 0) tmp[n++] = '.';
-    do { tmp[n++] = '0' + static_cast<int>(q % 10); q /= 10; } while (q && n < 38);
-    if (negv) tmp[n++] = '-';
+    if (v != v) {                       // printf: "nan"
+        tmp[n++] = 'n'; tmp[n++] = 'a'; tmp[n++] = 'n';
+    } else if (av > 1.0e300) {          // "inf" / "-inf" (digits are stored reversed)
+        tmp[n++] = 'f'; tmp[n++] = 'n'; tmp[n++] = 'i';
+        if (negv) tmp[n++] = '-';
+    } else {
+        double scale = 1.0;
+        for (int k = 0; k < prec; ++k) scale *= 10.0;
+        // exact decimal expansion of a binary float is finite: round-half-even on
+        // the exact product (av*scale is exact: 24 mantissa bits times 10^prec,
+        // prec <= 8, fits 53 bits)
+        const double scaled = av * scale;
+        unsigned long long q = static_cast<unsigned long long>(rint(scaled));
+        const bool neg = negv;          // printf keeps the sign of values that round to zero
+        for (int k = 0; k < prec; ++k) { tmp[n++] = '0' + static_cast<int>(q % 10); q /= 10; }
+        if (prec > 0) tmp[n++] = '.';
+        do { tmp[n++] = '0' + static_cast<int>(q % 10); q /= 10; } while (q && n < 38);
+        if (neg) tmp[n++] = '-';
+    }
     int pos = 0;
-    for (; pos < width - n; ++pos) p[pos] = ' ';
+    if (!left)
+        for (; pos < width - n; ++pos) p[pos] = ' ';
     for (int k = n - 1; k >= 0 && pos < width; --k) p[pos++] = tmp[k];
+    for (; pos < width; ++pos) p[pos] = ' ';
     if (crlf) { p[width] = '\r'; p[width + 1] = '\n'; }
     else p[width] = '\n';
 }

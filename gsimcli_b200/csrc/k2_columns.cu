@@ -208,6 +208,42 @@ struct K3Args {
     int32_t* detected;
 };
 
+// homog.py:191-239 for one (station, time step): fill, test, substitute
+struct K3Out { double filled, homog, flag; int hw; };
+
+__device__ __forceinline__ K3Out k3_apply(double c, double mean, double lo, double hi, double fa,
+                                          double fb, double fc, int method, double thr,
+                                          double nodata) {
+    // homog.py:200-201 -- NaN observations take the local mean
+    if (c != c) c = mean;
+    // homog.py:204 -- ~between(lperc, rperc), inclusive; NaN compares False.
+    // The bounds come from float32 realization values, the observation from
+    // float64 text: an observation that TIES a bound in the reference (both
+    // parsed from the same decimal, e.g. a DSS clamp value 0.7) must tie here
+    // too, so the observation is compared at the stack's precision
+    // (f32(0.7) == f32(0.7), whereas 0.7 > f32(0.7) would flag it).
+    const double cq = static_cast<double>(static_cast<float>(c));
+    const bool inside = (cq >= lo) && (cq <= hi);
+    const bool hw = !inside;
+    double fix;
+    switch (method) {
+    case GSB_METHOD_SKEWNESS:      // np.where(skew > thr, median, mean)
+        fix = (fc > thr) ? fa : fb;
+        break;
+    case GSB_METHOD_PERCENTILE:    // np.where(clim > rperc, rperc', lperc')
+        fix = (cq > hi) ? fa : fb;
+        break;
+    default:
+        fix = fa;
+    }
+    K3Out o;
+    o.filled = c;
+    o.homog = hw ? fix : c;        // clim.where(~hom_where, fixvalues)
+    o.flag = hw ? c : nodata;      // clim.where(hom_where, nodata)
+    o.hw = hw ? 1 : 0;
+    return o;
+}
+
 // one CTA per station; thread per time step
 __global__ void __launch_bounds__(128) k3_detect_kernel(const __grid_constant__ K3Args a) {
     __shared__ int s_det;
@@ -217,34 +253,57 @@ __global__ void __launch_bounds__(128) k3_detect_kernel(const __grid_constant__ 
     int det = 0;
     for (int t = threadIdx.x; t < a.dz; t += blockDim.x) {
         const long long e = static_cast<long long>(s) * a.dz + t;
-        double c = a.clim[e];
-        // homog.py:200-201 -- NaN observations take the local mean
-        if (c != c) c = a.mean[e];
-        const double lo = a.lperc[e], hi = a.rperc[e];
-        // homog.py:204 -- ~between(lperc, rperc), inclusive; NaN compares False.
-        // The bounds come from float32 realization values, the observation from
-        // float64 text: an observation that TIES a bound in the reference (both
-        // parsed from the same decimal, e.g. a DSS clamp value 0.7) must tie here
-        // too, so the observation is compared at the stack's precision
-        // (f32(0.7) == f32(0.7), whereas 0.7 > f32(0.7) would flag it).
-        const double cq = static_cast<double>(static_cast<float>(c));
-        const bool inside = (cq >= lo) && (cq <= hi);
-        const bool hw = !inside;
-        double fix;
-        switch (a.method) {
-        case GSB_METHOD_SKEWNESS:      // np.where(skew > thr, median, mean)
-            fix = (a.fix_c[e] > a.thr) ? a.fix_a[e] : a.fix_b[e];
-            break;
-        case GSB_METHOD_PERCENTILE:    // np.where(clim > rperc, rperc', lperc')
-            fix = (cq > hi) ? a.fix_a[e] : a.fix_b[e];
-            break;
-        default:
-            fix = a.fix_a[e];
-        }
-        a.filled[e] = c;
-        a.homog[e] = hw ? fix : c;       // clim.where(~hom_where, fixvalues)
-        a.flag[e] = hw ? c : a.nodata;   // clim.where(hom_where, nodata)
-        det += hw ? 1 : 0;
+        const K3Out o = k3_apply(a.clim[e], a.mean[e], a.lperc[e], a.rperc[e], a.fix_a[e],
+                                 a.fix_b[e], a.fix_c[e], a.method, a.thr, a.nodata);
+        a.filled[e] = o.filled;
+        a.homog[e] = o.homog;
+        a.flag[e] = o.flag;
+        det += o.hw;
+    }
+    atomicAdd(&s_det, det);
+    __syncthreads();
+    if (threadIdx.x == 0) a.detected[s] = s_det;
+}
+
+// the same step reading the K2c station tables where they lie on the device:
+// row (s, z) of a table is at ((zoff[z] + s * sstride) * C); one table for the
+// detection interval + mean, one for the substitute (they may be the same).
+// zoff / sstride describe either a plain [S][dz][C] table (zoff[z] = z,
+// sstride = dz) or the per-rank slabs an all-gather leaves behind
+// ([world][S][width][C]: zoff[z] = rank(z) * S * width + z - z0(rank), sstride = width).
+struct K3TabArgs {
+    const double* clim;
+    const double* table;
+    const double* fixtab;
+    const long long* zoff;
+    long long sstride;
+    int C, Cfix;
+    int c_mean, c_lperc, c_rperc, c_fa, c_fb, c_fc;
+    int S, dz, method;
+    double thr, nodata;
+    double* out;            // [3][S][dz]: filled, homog, flag
+    int32_t* detected;
+};
+
+__global__ void __launch_bounds__(128) k3_detect_table_kernel(const __grid_constant__ K3TabArgs a) {
+    __shared__ int s_det;
+    const int s = blockIdx.x;
+    if (threadIdx.x == 0) s_det = 0;
+    __syncthreads();
+    int det = 0;
+    const long long plane = static_cast<long long>(a.S) * a.dz;
+    for (int t = threadIdx.x; t < a.dz; t += blockDim.x) {
+        const long long e = static_cast<long long>(s) * a.dz + t;
+        const long long row = a.zoff[t] + static_cast<long long>(s) * a.sstride;
+        const double* tab = a.table + row * a.C;
+        const double* fix = a.fixtab + row * a.Cfix;
+        const K3Out o = k3_apply(a.clim[e], tab[a.c_mean], tab[a.c_lperc], tab[a.c_rperc],
+                                 fix[a.c_fa], fix[a.c_fb], a.c_fc >= 0 ? tab[a.c_fc] : 0.0,
+                                 a.method, a.thr, a.nodata);
+        a.out[e] = o.filled;
+        a.out[plane + e] = o.homog;
+        a.out[2 * plane + e] = o.flag;
+        det += o.hw;
     }
     atomicAdd(&s_det, det);
     __syncthreads();
@@ -313,9 +372,9 @@ __global__ void table_to_planes_kernel(const double* __restrict__ table, int npl
 
 int gsb_launch_k2_deep(gsb_stack* s, const GsbPlanes& pl, float nodata, int64_t n0, int64_t nn,
                        float* d_out, int64_t out_pitch, cudaStream_t st) {
-    // (the column kernel sorts in shared memory up to 51200 values; beyond that
-    // it would need the launcher scratch this function already uses)
-    GSB_REQUIRE(s->R <= 51200, "full-grid order statistics support R <= 51200 (got %lld)",
+    // up to 32768 values the column kernel sorts in shared memory; deeper columns
+    // would make it regrow the launcher scratch this function is using
+    GSB_REQUIRE(s->R <= 32768, "full-grid order statistics support R <= 32768 (got %lld)",
                 (long long)s->R);
     const int64_t chunk = 32768;
     const size_t ids_bytes = static_cast<size_t>(chunk) * 8;
@@ -356,9 +415,29 @@ int gsb_launch_k3_detect(const double* clim, const double* mean, const double* l
                          double nodata, double* filled, double* homog, double* flag,
                          int32_t* detected, cudaStream_t st) {
     if (S <= 0) return GSB_OK;
-    K3Args a{clim, mean, lperc, rperc, fix_a, fix_b, fix_c, S, dz, method,
-             thr, nodata, filled, homog, flag, detected};
+    // columns a method does not use may be NULL: they are read, never used
+    K3Args a{clim, mean, lperc, rperc, fix_a, fix_b ? fix_b : fix_a, fix_c ? fix_c : fix_a, S, dz,
+             method, thr, nodata, filled, homog, flag, detected};
     k3_detect_kernel<<<S, 128, 0, st>>>(a);
+    GSB_CUDA(cudaGetLastError());
+    return GSB_OK;
+}
+
+int gsb_launch_k3_detect_table(const double* clim, const double* table, const double* fixtab,
+                               const int64_t* zoff, int64_t sstride, int C, int Cfix, int c_mean,
+                               int c_lperc, int c_rperc, int c_fa, int c_fb, int c_fc, int S, int dz,
+                               int method, double thr, double nodata, double* out,
+                               int32_t* detected, cudaStream_t st) {
+    if (S <= 0) return GSB_OK;
+    K3TabArgs a;
+    a.clim = clim; a.table = table; a.fixtab = fixtab;
+    a.zoff = reinterpret_cast<const long long*>(zoff); a.sstride = sstride;
+    a.C = C; a.Cfix = Cfix;
+    a.c_mean = c_mean; a.c_lperc = c_lperc; a.c_rperc = c_rperc;
+    a.c_fa = c_fa; a.c_fb = c_fb; a.c_fc = c_fc;
+    a.S = S; a.dz = dz; a.method = method; a.thr = thr; a.nodata = nodata;
+    a.out = out; a.detected = detected;
+    k3_detect_table_kernel<<<S, 128, 0, st>>>(a);
     GSB_CUDA(cudaGetLastError());
     return GSB_OK;
 }

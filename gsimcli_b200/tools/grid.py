@@ -189,11 +189,47 @@ class GridArr(object):
     def save(self, outfile, varname='var', header=True):
         """Write the grid: 3 header lines then ``%-10.6f`` per node
         (grid.py:328-347)."""
-        with open(outfile, 'w') as fid:
+        val = np.asarray(self.val)
+        body = None
+        if val.ndim == 1 and val.size >= GridArr.DEVICE_SAVE_MIN:
+            body = self._encode_on_device(val)
+        with open(outfile, 'wb') as fid:
             if header:
                 base = os.path.splitext(os.path.basename(outfile))[0]
-                fid.write(base + '\n1\n' + varname + '\n')
-            np.savetxt(fid, self.val, fmt='%-10.6f')
+                fid.write((base + '\n1\n' + varname + '\n').encode())
+            if body is not None:
+                fid.write(body)
+            else:
+                np.savetxt(fid, self.val, fmt='%-10.6f')
+
+    # maps of this size and larger are formatted by the K1 encoder on the GPU
+    DEVICE_SAVE_MIN = 1 << 16
+
+    @staticmethod
+    def _encode_on_device(val):
+        """``np.savetxt(fmt='%-10.6f')`` of a float32-representable vector, the
+        decimal conversion done by the device encoder (the statistics maps are
+        float32 widened to float64, so nothing is lost).  Records are written
+        24 characters wide, left-justified; the host only trims each to
+        ``max(10, len)`` characters -- byte-identical to the reference's output.
+        Returns None (host formatting) when the values are not exactly float32
+        or no device is present."""
+        v32 = val.astype(np.float32)
+        with np.errstate(invalid='ignore'):
+            exact = (v32.astype(np.float64) == val) | (np.isnan(val) & np.isnan(v32))
+        if not exact.all() or np.abs(v32[np.isfinite(v32)]).max(initial=0.0) >= 1e12:
+            return None
+        try:
+            _capi.require_device()
+        except RuntimeError:
+            return None
+        W = 24
+        rec = _capi.encode_values(v32, W, 6, crlf=False, left=True)      # [n][W + 1]
+        used = (rec[:, :W] != 32)
+        length = np.maximum(10, W - np.argmax(used[:, ::-1], axis=1))
+        keep = np.arange(W + 1)[None, :] < length[:, None]
+        keep[:, W] = True                                                # the newline
+        return rec[keep].tobytes()
 
     def drill(self, wellxy, save=False, outfile=None, header=True):
         """Vertical extraction at world coordinates ``wellxy``.
@@ -299,12 +335,13 @@ class GridFiles(object):
         self.nfiles = len(paths)
         stack = _capi.Stack(self.nfiles, int(n1) - int(n0), device)
         try:
-            for r, path in enumerate(paths):
-                try:
-                    text = np.fromfile(path, dtype=np.uint8)
-                except (IOError, OSError):
+            for path in paths:
+                if not os.path.isfile(path):
                     raise IOError('File {0} not found.'.format(path))
-                self._decode_file(stack, r, text)
+            if not self._decode_files_pipelined(stack, paths):
+                for r, path in enumerate(paths):
+                    text = np.fromfile(path, dtype=np.uint8)
+                    self._decode_file(stack, r, text)
         except Exception:
             stack.close()
             self.files, self.nfiles = [], 0
@@ -332,6 +369,147 @@ class GridFiles(object):
             except ValueError:
                 pass        # coincidental size match: decode as general text
         stack.decode_text(r, text, self.header, 0, self.node0, 0, nn)
+
+    def _probe_layout(self, path):
+        """(body offset, record width) of a fixed-width realization file
+        (every data line the same number of bytes, e.g. the 14 B/node of
+        '%12.4f\\r\\n', interface/gui.py:1414), else None."""
+        size = os.path.getsize(path)
+        with open(path, 'rb') as fh:
+            head = np.frombuffer(fh.read(8192), dtype=np.uint8)
+        body = 0
+        for _ in range(self.header):
+            nl = np.flatnonzero(head[body:] == 10)
+            if nl.size == 0:
+                return None
+            body += int(nl[0]) + 1
+        nl = np.flatnonzero(head[body:] == 10)
+        if nl.size == 0:
+            return None
+        width = int(nl[0]) + 1
+        if width < 2 or width > 64 or size - body != self.cells * width:
+            return None
+        return body, width
+
+    def _decode_files_pipelined(self, stack, paths, slots=3):
+        """Fixed-width files: only the byte range of this stack's nodes is read
+        (O(1) offsets), into a ring of pinned buffers; the upload and the K1
+        decode of file r run on the ring slot's stream while files r+1.. are
+        being read.  One synchronisation at the end (the reference's
+        per-line ``float()`` errors surface there as ValueError).  Returns False
+        when the files are not fixed-width (general decoder, file by file)."""
+        import torch
+        from concurrent.futures import ThreadPoolExecutor
+        if not paths:
+            return True
+        lay = self._probe_layout(paths[0])
+        if lay is None:
+            return False
+        body, width = lay
+        for path in paths[1:]:
+            if self._probe_layout(path) != lay:
+                return False
+        nn = stack.N
+        nbytes = nn * width
+        offset = body + self.node0 * width
+        dev = torch.device('cuda', self.device)
+        ring = []
+        for _ in range(min(slots, len(paths))):
+            ring.append({
+                'pin': torch.empty(nbytes, dtype=torch.uint8).pin_memory(),
+                'dev': torch.empty(nbytes + 64, dtype=torch.uint8, device=dev),
+                'stream': torch.cuda.Stream(device=dev),
+                'free': None})
+        bad = torch.full((len(paths),), -1, dtype=torch.int64, device=dev)
+        L = _capi.lib()
+
+        def read_into(path, pin):
+            with open(path, 'rb', buffering=0) as fh:
+                fh.seek(offset)
+                got = fh.readinto(memoryview(pin.numpy()))
+            if got != nbytes:
+                raise ValueError('{0}: expected {1} bytes of records, read {2}'
+                                 .format(path, nbytes, got))
+
+        with ThreadPoolExecutor(max_workers=len(ring)) as pool:
+            pending = {}
+            for r in range(min(len(ring), len(paths))):
+                pending[r] = pool.submit(read_into, paths[r], ring[r]['pin'])
+            for r, path in enumerate(paths):
+                slot = ring[r % len(ring)]
+                pending.pop(r).result()
+                st = slot['stream']
+                with torch.cuda.stream(st):
+                    slot['dev'][:nbytes].copy_(slot['pin'], non_blocking=True)
+                _capi.check(L.gsb_decode_text_device(
+                    stack.handle, r, slot['dev'].data_ptr(), nbytes, 0, width, 0, 0,
+                    nn, bad[r:].data_ptr(), st.cuda_stream))
+                ev = torch.cuda.Event()
+                ev.record(st)
+                nxt = r + len(ring)
+                if nxt < len(paths):
+                    # the slot's pinned buffer is free once its upload is done
+                    def chained(path=paths[nxt], pin=slot['pin'], ev=ev):
+                        ev.synchronize()
+                        read_into(path, pin)
+                    pending[nxt] = pool.submit(chained)
+        torch.cuda.synchronize(dev)
+        badh = bad.cpu().numpy()
+        if (badh >= 0).any():
+            r = int(np.argmax(badh >= 0))
+            raise ValueError('could not convert string to float: data line {0} '
+                             'of {1}'.format(int(badh[r]) + self.node0, paths[r]))
+        return True
+
+    @classmethod
+    def from_pinned_text(cls, texts, dims, first_coord, cells_size, no_data,
+                         line_width, device=0, node_range=None, streams=3):
+        """Extension (BASELINE config 4): build the stack from realization text
+        that already sits in pinned host memory.  ``texts`` is a list of uint8
+        torch tensors (pinned), each holding the fixed-width records
+        (``line_width`` bytes per node, no header) of this stack's node range of
+        one realization.  Upload and K1 decode of the files rotate over
+        ``streams`` streams and device staging buffers, so the H2D copy of one
+        file overlaps the decode of the previous ones; nothing synchronises
+        until the end."""
+        import torch
+        self = cls()
+        self._geometry(dims, first_coord, cells_size, no_data, 0)
+        self.device = device
+        n0, n1 = (0, self.cells) if node_range is None else node_range
+        self.node0 = int(n0)
+        self.sharded = node_range is not None
+        self.nfiles = len(texts)
+        nn = int(n1 - n0)
+        stack = _capi.Stack(self.nfiles, nn, device)
+        dev = torch.device('cuda', device)
+        nbytes = nn * int(line_width)
+        ring = [(torch.empty(nbytes + 64, dtype=torch.uint8, device=dev),
+                 torch.cuda.Stream(device=dev)) for _ in range(max(1, streams))]
+        bad = torch.full((max(1, len(texts)),), -1, dtype=torch.int64, device=dev)
+        L = _capi.lib()
+        try:
+            for r, t in enumerate(texts):
+                if t.numel() != nbytes:
+                    raise ValueError('realization {0}: {1} bytes of text, expected '
+                                     '{2}'.format(r, t.numel(), nbytes))
+                dbuf, st = ring[r % len(ring)]
+                with torch.cuda.stream(st):
+                    dbuf[:nbytes].copy_(t, non_blocking=True)
+                _capi.check(L.gsb_decode_text_device(
+                    stack.handle, r, dbuf.data_ptr(), nbytes, 0, int(line_width), 0, 0,
+                    nn, bad[r:].data_ptr(), st.cuda_stream))
+            torch.cuda.synchronize(dev)
+            badh = bad.cpu().numpy()
+            if (badh >= 0).any():
+                r = int(np.argmax(badh >= 0))
+                raise ValueError('could not convert string to float: data line '
+                                 '{0} of realization {1}'.format(int(badh[r]), r))
+        except Exception:
+            stack.close()
+            raise
+        self._stack = stack
+        return self
 
     @classmethod
     def from_array(cls, stack, dims, first_coord, cells_size, no_data,

@@ -240,6 +240,225 @@ def detect_many(grids, obs_list, rad=0, method='mean', prob=0.95,
     return out
 
 
+class DetectPlan(object):
+    """Extension: the station path of one network prepared once and kept on
+    the device, so that a step is launches only.
+
+    ``detect`` does, per call, host work that depends on the candidates but not
+    on the realizations (load / clean the point-sets, expand them to the grid's
+    time axis, find the station nodes -- homog.py:169-188, 279-337,
+    grid.py:793-804).  The plan does it once and uploads the result: node ids,
+    observations (NaN where missing: K3 fills those with the local mean,
+    homog.py:200-201).  ``enqueue`` then runs, on one stream and without a host
+    round trip,
+
+        K2c  (gsb_stats_columns_device: local PDFs at the station nodes)
+        [all-gather of the per-rank table slabs, NCCL, node-sharded stacks]
+        K3   (gsb_detect_table: fill / flag / substitute)
+        D2H  of the [3][S][dz] result + the S detection counts (pinned)
+
+    and ``fetch`` waits for that copy.  ``results`` assembles the reference's
+    return values (point-sets) from it -- host glue, outside the step.
+    """
+
+    def __init__(self, grids, obs_list, rad=0, method='mean', prob=0.95,
+                 skewness=None, percentile=None, header=True,
+                 optional_stats=None, group=None):
+        import torch
+        self.torch = torch
+        self.grids, self.rad, self.method = grids, rad, method
+        self.prob, self.skewness = prob, skewness
+        self.optional_stats = optional_stats
+        sel = _select_stats(method, skewness, optional_stats)
+        self.flags = _capi.flags_from(**sel)
+        names = [nm for key, nm in gr._AREA_COLUMNS if sel.get(key)]
+        names += ['lperc', 'rperc']
+        self.names = names
+        C = len(names)
+        col = names.index
+        if method == 'mean':
+            c_fa, c_fb, c_fc = col('mean'), col('mean'), -1
+        elif method == 'median':
+            c_fa, c_fb, c_fc = col('median'), col('median'), -1
+        elif method == 'skewness':
+            c_fa, c_fb, c_fc = col('median'), col('mean'), col('skewness')
+        else:
+            c_fa, c_fb, c_fc = col('rperc'), col('lperc'), -1
+        self.two_tables = method == 'percentile' and percentile != prob
+        self.percentile = percentile
+        self.cidx = (col('mean'), col('lperc'), col('rperc'), c_fa, c_fb, c_fc)
+        if self.two_tables:          # the correction interval has its own table
+            self.cidx = (col('mean'), col('lperc'), col('rperc'), 1, 0, -1)
+        # ---- host preparation, once
+        stack = grids._need_stack()
+        dz = grids.dz
+        self.prepared, self.fns, self.filled_obs, self.locs = [], [], [], []
+        clim = np.empty((len(obs_list), dz))
+        nans = np.full(dz, np.nan)
+        for s, o in enumerate(obs_list):
+            obs, xy, nodatas = _prepare_obs(o, grids, header)
+            fn = 0
+            if obs.array().shape[0] < dz:
+                obs, fn = fill_station(obs, nans, grids.zi, grids.zi + dz,
+                                       grids.cellz, header)
+            _check_series(obs, dz)
+            clim[s] = obs.array()[:, obs.columns().index('clim')]
+            self.prepared.append((obs, xy, nodatas))
+            self.fns.append(fn)
+            self.locs.append(xy)
+        S = self.S = len(obs_list)
+        self.nodata = self.prepared[0][0].nodata if S else -999.9
+        nodes, ids = [], []
+        for loc in self.locs:
+            node, nid = grids._area_nodes(loc, rad)
+            nodes.append(node)
+            ids.append(nid)
+        self.nodes = nodes
+        kmax = max(i.shape[1] for i in ids) if ids else 1
+        ids = (np.stack([np.pad(i, ((0, 0), (0, kmax - i.shape[1])),
+                                constant_values=-1) for i in ids])
+               if ids else np.zeros((0, dz, 1), dtype=np.int64))
+        self.K = kmax
+        # ---- layer slabs of the ranks (whole time layers, gathered once)
+        dev = torch.device('cuda', grids.device)
+        self.dev = dev
+        per = grids.dx * grids.dy
+        self.group = group
+        self.world = 1
+        if grids.sharded:
+            import torch.distributed as td
+            if not (td.is_available() and td.is_initialized()):
+                raise RuntimeError(
+                    'this stack holds a node range only: the station tables of '
+                    'the other ranks are needed (torch.distributed is not '
+                    'initialised)')
+            if grids.node0 % per or (stack.N % per and grids.node0 + stack.N
+                                     != per * dz):
+                raise ValueError('a node-sharded stack must hold whole time '
+                                 'layers (node range {0}..{1}, {2} nodes per '
+                                 'layer)'.format(grids.node0,
+                                                 grids.node0 + stack.N, per))
+            self.world = td.get_world_size(group)
+            z0 = grids.node0 // per
+            z1 = min(dz, -(-(grids.node0 + stack.N) // per))
+            mine = torch.tensor([z0, z1], dtype=torch.int64, device=dev)
+            allr = torch.empty((self.world, 2), dtype=torch.int64, device=dev)
+            td.all_gather_into_tensor(allr, mine, group=group)
+            ranges = [(int(a), int(b)) for a, b in allr.cpu().tolist()]
+            cover = np.zeros(dz, dtype=np.int64)
+            for a, b in ranges:
+                cover[a:b] += 1
+            if not np.all(cover == 1):
+                raise ValueError('the ranks\' time-layer slabs {0} do not tile '
+                                 'the {1} layers exactly once'.format(ranges, dz))
+        else:
+            z0, z1 = 0, dz
+            ranges = [(0, dz)]
+        self.z0, self.z1 = z0, z1
+        width = self.width = max(b - a for a, b in ranges)
+        # this rank's layers, padded to the widest slab with absent nodes
+        mine_ids = np.full((S, width, kmax), -1, dtype=np.int64)
+        mine_ids[:, :z1 - z0] = ids[:, z0:z1]
+        zoff = np.empty(dz, dtype=np.int64)
+        for r, (a, b) in enumerate(ranges):
+            zoff[a:b] = r * S * width + np.arange(b - a)
+        self.C = C
+        f64 = torch.float64
+        self.d_ids = torch.from_numpy(mine_ids).to(dev)
+        self.d_zoff = torch.from_numpy(zoff).to(dev)
+        self.d_clim = torch.from_numpy(clim).to(dev)
+        self.d_part = torch.empty((S, width, C), dtype=f64, device=dev)
+        self.d_full = (torch.empty((self.world, S, width, C), dtype=f64, device=dev)
+                       if self.world > 1 else self.d_part)
+        if self.two_tables:
+            self.d_part2 = torch.empty((S, width, 2), dtype=f64, device=dev)
+            self.d_full2 = (torch.empty((self.world, S, width, 2), dtype=f64,
+                                        device=dev)
+                            if self.world > 1 else self.d_part2)
+        self.d_out = torch.empty((3, S, dz), dtype=f64, device=dev)
+        self.d_det = torch.zeros((S,), dtype=torch.int32, device=dev)
+        self.h_out = torch.empty((3, S, dz), dtype=f64).pin_memory()
+        self.h_det = torch.zeros((S,), dtype=torch.int32).pin_memory()
+        self.done = torch.cuda.Event()
+        self._q = np.zeros(0, dtype=np.float64)
+
+    def enqueue(self, stream=None):
+        """Enqueue one station step on ``stream`` (a ``torch.cuda.Stream``;
+        default: the current stream).  No host synchronisation."""
+        torch = self.torch
+        L = _capi.lib()
+        st = stream if stream is not None else torch.cuda.current_stream(self.dev)
+        h = st.cuda_stream
+        stack = self.grids._need_stack()
+        S, dz, C = self.S, self.grids.dz, self.C
+        if S == 0:
+            return
+        qp = self._q.ctypes.data_as(_capi.p_f64)
+        nd = self.grids.nodata
+        _capi.check(L.gsb_stats_columns_device(
+            stack.handle, self.d_ids.data_ptr(), S, self.width, self.K, self.flags,
+            self.prob, qp, 0, nd, self.d_part.data_ptr(), h))
+        if self.two_tables:
+            _capi.check(L.gsb_stats_columns_device(
+                stack.handle, self.d_ids.data_ptr(), S, self.width, self.K,
+                _capi.PERC, self.percentile, qp, 0, nd, self.d_part2.data_ptr(), h))
+        if self.world > 1:
+            import torch.distributed as td
+            with torch.cuda.stream(st):
+                td.all_gather_into_tensor(self.d_full, self.d_part, group=self.group)
+                if self.two_tables:
+                    td.all_gather_into_tensor(self.d_full2, self.d_part2,
+                                              group=self.group)
+        fix = self.d_full2 if self.two_tables else self.d_full
+        cm, cl, cr, fa, fb, fc = self.cidx
+        _capi.check(L.gsb_detect_table(
+            self.d_clim.data_ptr(), self.d_full.data_ptr(), fix.data_ptr(),
+            self.d_zoff.data_ptr(), self.width, C, 2 if self.two_tables else C,
+            cm, cl, cr, fa, fb, fc, S, dz, _capi.METHODS[self.method],
+            float(self.skewness or 0.0), self.nodata, self.d_out.data_ptr(),
+            self.d_det.data_ptr(), self.grids.device, h))
+        with torch.cuda.stream(st):
+            self.h_out.copy_(self.d_out, non_blocking=True)
+            self.h_det.copy_(self.d_det, non_blocking=True)
+            self.done.record(st)
+
+    def fetch(self):
+        """Wait for the last enqueued step; ``(filled, homog, flag, detected)``
+        as NumPy views of the pinned result buffers."""
+        self.done.synchronize()
+        o = self.h_out.numpy()
+        return o[0], o[1], o[2], self.h_det.numpy()
+
+    def table(self):
+        """The full ``[S][dz][C]`` station table of the last step on the host
+        (columns ``self.names``)."""
+        torch = self.torch
+        self.done.synchronize()
+        full = self.d_full.cpu().numpy().reshape(-1, self.C)
+        zoff = self.d_zoff.cpu().numpy()
+        rows = zoff[None, :] + np.arange(self.S)[:, None] * self.width
+        return full[rows]
+
+    def results(self, flag=True):
+        """The reference's return values for the last step: a list of
+        ``(homogenised PointSet, detected_number, missing_data)``."""
+        filled, homog, flagcol, det = self.fetch()
+        table = self.table()
+        out = []
+        for s, (obs, xy, nodatas) in enumerate(self.prepared):
+            local = {nm: table[s, :, i] for i, nm in enumerate(self.names)}
+            # each call assembles from a fresh copy of the prepared series
+            fresh = gr.PointSet(obs.name, obs.nodata, obs.nvars, list(obs.varnames),
+                                obs.array().copy())
+            fresh.set_array(fresh.array(), obs.row_index())
+            hom, dn = _finish(fresh, local, None, self.method, self.skewness,
+                              (filled[s].copy(), homog[s].copy(), flagcol[s].copy(),
+                               det[s]), flag, self.optional_stats, self.grids, xy,
+                              self.rad)
+            out.append((hom, dn, self.fns[s] + nodatas))
+        return out
+
+
 def detect_sweep(grids, obs_list, probs, rad=0, method='mean', skewness=None,
                  flag=True, header=True, optional_stats=None, stream=None):
     """Extension: ``detect_many`` for several detection probabilities at once
@@ -315,6 +534,48 @@ def detect_sweep(grids, obs_list, probs, rad=0, method='mean', skewness=None,
     return out
 
 
+def detect_batch(networks, probs, rad=0, method='mean', skewness=None,
+                 flag=True, header=True, optional_stats=None, group=None):
+    """Extension (BASELINE config 5, the batch mode of
+    launchers/method_classic.py:461-534 with its loop at :506): many independent
+    (stack, candidate stations) problems, each with a sweep of detection
+    probabilities.
+
+    ``networks`` is a list of ``(make_grids, obs_list)``; ``make_grids(device)``
+    returns the network's ``GridFiles`` on that device (called only on the rank
+    that owns the network, so that 100 stacks never have to be resident at
+    once) and is dumped after use.  Whole networks are dealt round-robin to the
+    ranks of ``torch.distributed`` (replicas: no data-path collective); the
+    results are exchanged at the end with one object gather.  Returns, on
+    every rank, ``[{prob: [detect-style tuples]} for each network]``.
+    """
+    import torch
+    import torch.distributed as td
+    dist_on = td.is_available() and td.is_initialized()
+    world = td.get_world_size(group) if dist_on else 1
+    rank = td.get_rank(group) if dist_on else 0
+    device = torch.cuda.current_device()
+    mine = {}
+    for i, (make_grids, obs_list) in enumerate(networks):
+        if i % world != rank:
+            continue
+        grids = make_grids(device)
+        try:
+            mine[i] = detect_sweep(grids, obs_list, probs, rad=rad, method=method,
+                                   skewness=skewness, flag=flag, header=header,
+                                   optional_stats=optional_stats)
+        finally:
+            grids.dump()
+    if world == 1:
+        return [mine[i] for i in range(len(networks))]
+    parts = [None] * world
+    td.all_gather_object(parts, mine, group=group)
+    merged = {}
+    for part in parts:
+        merged.update(part)
+    return [merged[i] for i in range(len(networks))]
+
+
 def _check_series(obs, dz):
     """The filled series must have one row per grid time step.  The reference
     fails in pandas when it does not (`meanvalues.index = obs.values.index`,
@@ -387,7 +648,9 @@ def fill_station(pset_file, values, time_min, time_max, time_step=1,
 def list_stations(pset_file, header=True, variables=None):
     """Station ids present in a point-set (homog.py:340-380)."""
     pset = gr.loadcheck(pset_file, header)
-    ids = pset.values['station'].unique()
+    if variables:
+        pset.flush_varnames(variables)
+    ids = np.unique(pset.values['station'])         # sorted, like the reference
     return [int(i) for i in ids]
 
 
@@ -424,3 +687,128 @@ def update_station(stations_pset, station, header=True):
             pset.add_var(np.repeat(np.nan, pset.values.shape[0]), var)
     pset.values.update(station.values)
     return pset
+
+
+def station_order(method, pset_file=None, nd=-999.9, header=True,
+                  userset=None, ascending=False, md_last=True):
+    """Order in which the stations of a network are homogenised
+    (homog.py:548-623).  ``method``: 'random', 'sorted', 'variance' (variance
+    of each station's series), 'network deviation' (|station mean - network
+    mean|) or 'user' (``userset`` as given).  Missing data (``nd``) is ignored
+    in the statistics; stations without any statistic go last (``md_last``) or
+    first."""
+    from random import shuffle
+    pset = None
+    if pset_file is not None:
+        if isinstance(pset_file, gr.PointSet):
+            pset = pset_file
+        else:
+            pset = gr.PointSet(psetpath=pset_file, nodata=nd, header=header)
+    if method == 'user' and userset:
+        return userset
+    if pset is None:
+        if method in ('variance', 'network deviation', 'random', 'sorted'):
+            raise TypeError('Method {0} requires the stations point-set'
+                            .format(method))
+        raise TypeError('Method {0} not understood or invalid userset ({1}).'
+                        .format(method, userset))
+    stations_list = list_stations(pset, header=header)
+    na_position = 'last' if md_last else 'first'
+    if method == 'random':
+        shuffle(stations_list)
+    elif method == 'sorted':
+        stations_list.sort(reverse=not ascending)
+    elif method == 'variance':
+        values = pset.values.replace(nd, np.nan)
+        varsort = values.groupby('station', sort=False).clim.var()
+        varsort = varsort.sort_values(ascending=ascending, na_position=na_position)
+        stations_list = list(varsort.index)
+    elif method == 'network deviation':
+        values = pset.values.replace(nd, np.nan)
+        stations_mean = values.groupby('station', sort=False).clim.mean()
+        network_dev = ((stations_mean - values.clim.mean()).abs()
+                       .sort_values(ascending=ascending, na_position=na_position))
+        stations_list = list(network_dev.index)
+    else:
+        raise TypeError('Method {0} not understood or invalid userset ({1}).'
+                        .format(method, userset))
+    return stations_list
+
+
+def save_output(pset_file, outfile, fformat='gsimcli', outvars=None,
+                header=True, network_split=True, save_stations=False,
+                keys=None, append_year=False):
+    """Write homogenisation results (homog.py:626-760).
+
+    ``fformat``: 'gsimcli' -- CSV indexed by year with the columns
+    ``<station>_clim, <station>_Flag`` (+ optional statistics) per station;
+    'normal' -- CSV of the point-set's columns (``outvars``: column indices);
+    'gslib' -- GSLIB point-set with header.  ``save_stations`` adds
+    ``<outfile>_stations.csv`` with the station ids and coordinates.
+    ('cost-home' is not implemented in the reference either.)"""
+    import csv
+    import os
+    if isinstance(pset_file, gr.PointSet):
+        pset = pset_file
+    else:
+        pset = gr.PointSet()
+        pset.load(pset_file, header)
+
+    if fformat == 'normal':
+        with open(outfile, 'w', newline='') as csvfile:
+            out = csv.writer(csvfile, dialect='excel')
+            if not outvars:
+                out.writerow(pset.varnames)
+                out.writerows(pset.values.values.tolist())
+            else:
+                out.writerow([pset.varnames[i] for i in outvars])
+                out.writerows(pset.values.iloc[:, np.array(outvars)].values.tolist())
+    elif fformat == 'gsimcli':
+        stations = list_stations(pset, header)
+        cols = ['clim', 'Flag']
+        cols += sorted(set(pset.varnames)
+                       - set(['x', 'y', 'time', 'station', 'clim', 'Flag']))
+        cols = [c for c in cols if c in pset.values.columns]
+        csvheader = [str(st) + '_' + var for st in stations for var in cols]
+        vals = pset.values
+        years = np.arange(vals['time'].min(), vals['time'].max() + 1)
+        outdf = pd.DataFrame(index=years, columns=csvheader, dtype=object)
+        for i, st in enumerate(stations):
+            sel = vals['station'] == st
+            temp = vals[sel][cols].copy()
+            temp.index = vals[sel]['time']
+            temp.columns = csvheader[len(cols) * i:len(cols) * (i + 1)]
+            outdf.update(temp)
+        if append_year:
+            raise NotImplementedError
+        outdf.dropna(axis=1, how='all', inplace=True)
+        outdf.to_csv(outfile, index_label='year')
+    elif fformat.lower() == 'gslib':
+        if network_split and 'network' in pset.varnames:
+            networks = pset.values['network'].unique()
+            names = [v for v in pset.varnames if v != 'network']
+            for nw in networks:
+                part = pset.values[pset.values['network'] == nw].drop('network', axis=1)
+                temp = gr.PointSet(pset.name + ' network: ' + str(nw), pset.nodata,
+                                   len(names), list(names), part)
+                base, ext = os.path.splitext(outfile)
+                temp.save(base + '_' + str(nw) + ext, header=True)
+        else:
+            pset.save(outfile, header=True)
+    else:
+        raise ValueError('unknown output format {0!r}'.format(fformat))
+
+    if save_stations:
+        stations = list_stations(pset, header)
+        stations_out = os.path.join(
+            os.path.dirname(outfile),
+            os.path.splitext(os.path.basename(outfile))[0] + '_stations.csv')
+        rows = []
+        for st in stations:
+            temp = pset.values[pset.values['station'] == st]
+            rows.append(temp.loc[temp.first_valid_index(), ['x', 'y']].values)
+        stationsdf = pd.DataFrame(np.array(rows, dtype=float).reshape(len(stations), 2),
+                                  index=stations, columns=['x', 'y'])
+        if keys:
+            stationsdf = stationsdf.join(pd.read_csv(keys, sep='\t', index_col=0))
+        stationsdf.to_csv(stations_out, index_label='Station')

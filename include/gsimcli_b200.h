@@ -46,7 +46,10 @@ enum {
     GSB_EINVAL = 2,
     GSB_EPARSE = 3,
     GSB_ECUDA = 4,
-    GSB_ENCCL = 5,
+    GSB_ENCCL = 5,   /* reserved: the library exports no collective.  The only exchange of
+                        the path -- the all-gather of the per-station tables of a
+                        node-sharded stack -- is the binding's job (torch.distributed
+                        on the device buffers gsb_stats_columns_device fills) */
     GSB_ENOMEM = 6
 };
 
@@ -94,7 +97,10 @@ int gsb_stack_info(const gsb_stack* s, int64_t* R, int64_t* N, int64_t* pitch,
                    int* device);
 /* tuning knobs.  "k2_sm_reserve" = number of SMs the full-grid kernel leaves
  * free (default 0) so that station-column / detect launches on another stream
- * run concurrently with it instead of queueing behind its persistent CTAs. */
+ * run concurrently with it instead of queueing behind its persistent CTAs.
+ * Tests and profiling only: "k2_algo" selects the full-grid kernel (0 = default,
+ * 2 = register bitonic for every R, 3 = register tile), "k2_nw" the warps per
+ * CTA of the register-tile kernel, "k2_stats" enables gsb_debug_cs_counters. */
 int gsb_stack_set_option(gsb_stack* s, const char* key, int64_t value);
 /* diagnostic: number of 32-node tiles of the last gsb_stats_grid call on this
  * stack that the register-tile kernel handed to the counting-sort kernel
@@ -110,6 +116,11 @@ int gsb_stack_device_ptr(const gsb_stack* s, void** dptr);
 int gsb_stack_upload_f32(gsb_stack* s, int64_t r0, int64_t nr, int64_t n0,
                          int64_t nn, const float* host, int64_t host_pitch,
                          void* stream);
+/* enqueue-only form of the upload: `host` must be pinned and stay untouched
+ * until `stream` has passed the copy (the synchronous form above waits). */
+int gsb_stack_upload_f32_async(gsb_stack* s, int64_t r0, int64_t nr,
+                               int64_t n0, int64_t nn, const float* host,
+                               int64_t host_pitch, void* stream);
 int gsb_stack_download_f32(const gsb_stack* s, int64_t r0, int64_t nr,
                            int64_t n0, int64_t nn, float* host,
                            int64_t host_pitch, void* stream);
@@ -139,9 +150,11 @@ int gsb_decode_text_device(gsb_stack* s, int64_t r, const char* dtext,
                            int64_t first_line, int64_t n0, int64_t nlines,
                            int64_t* d_bad_line, void* stream);
 /* inverse of K1 for synthetic inputs and GridArr.save-style output
- * (grid.py:341-347): row r, nodes [n0, n0+nn) -> fixed-width text
- * ('%<width>.<prec>f' + eol) written to a DEVICE buffer of
- * nn*(width+eol_len) bytes. */
+ * (grid.py:341-347): row r, nodes [n0, n0+nn) -> fixed-width records
+ * ('%<width>.<prec>f' + eol, correctly rounded like printf; "nan" / "inf" for
+ * non-finite values) written to a DEVICE buffer of nn*(width+eol_len) bytes.
+ * `crlf` bit 0: EOL is "\r\n" instead of "\n"; bit 1: left-justified
+ * ('%-<width>.<prec>f', the np.savetxt format of GridArr.save). */
 int gsb_encode_text_device(const gsb_stack* s, int64_t r, int64_t n0,
                            int64_t nn, int width, int prec, int crlf,
                            char* dtext, void* stream);
@@ -183,6 +196,15 @@ int gsb_stats_columns(gsb_stack* s, const int64_t* node_ids, int S, int dz,
                       int K, uint32_t flags, double p, const double* q, int nq,
                       float nodata, double* table, int table_on_device,
                       void* stream);
+/* same reduction, everything resident: d_node_ids and d_table are DEVICE
+ * pointers, nothing is validated or copied, the call only enqueues.  This is
+ * the step form of the station path: the ids of a network's stations are
+ * uploaded once, the table stays on the device for gsb_detect_table (and for
+ * the NCCL gather of a node-sharded stack). */
+int gsb_stats_columns_device(gsb_stack* s, const int64_t* d_node_ids, int S,
+                             int dz, int K, uint32_t flags, double p,
+                             const double* q, int nq, float nodata,
+                             double* d_table, void* stream);
 /* raw extraction at station coordinates (`save=True`, grid.py:851-867):
  * values HOST float32 [S][dz][K][R] in realization order. */
 int gsb_extract_columns(gsb_stack* s, const int64_t* node_ids, int S, int dz,
@@ -209,9 +231,27 @@ int gsb_detect(const double* clim, const double* mean, const double* lperc,
                double nodata, double* filled, double* homog, double* flag,
                int32_t* detected, int on_device, int device, void* stream);
 
+/* K3 reading the station tables where gsb_stats_columns_device (and, on a
+ * node-sharded stack, the all-gather of the per-rank slabs) left them; every
+ * pointer is DEVICE, the call only enqueues.  Row (s, z) of `d_table` (C
+ * columns) and `d_fixtab` (Cfix columns; the same table unless the percentile
+ * method corrects with another interval, homog.py:222-233) starts at element
+ * (d_zoff[z] + s * sstride) * C: a plain [S][dz][C] table has d_zoff[z] = z,
+ * sstride = dz; gathered slabs [world][S][width][C] have d_zoff[z] =
+ * rank(z) * S * width + z - z0(rank(z)), sstride = width.  c_* are column
+ * indices: c_mean, c_lperc, c_rperc in d_table; c_fa, c_fb in d_fixtab with
+ * the meaning of fix_a / fix_b above; c_fc (skewness, -1 when unused) in
+ * d_table.  d_out is [3][S][dz]: filled, homog, flag. */
+int gsb_detect_table(const double* d_clim, const double* d_table,
+                     const double* d_fixtab, const int64_t* d_zoff,
+                     int64_t sstride, int C, int Cfix, int c_mean, int c_lperc,
+                     int c_rperc, int c_fa, int c_fb, int c_fc, int S, int dz,
+                     int method, double thr, double nodata, double* d_out,
+                     int32_t* d_detected, int device, void* stream);
+
 /* ---- diagnostics ----------------------------------------------------------
- * Counters of the counting-sort K2 kernel, accumulated only while the
- * environment variable GSB_K2_STATS is non-zero: out[0] columns reduced,
+ * Counters of the counting-sort K2 kernel, accumulated only while the stack
+ * option "k2_stats" is non-zero: out[0] columns reduced,
  * [1] columns that held an over-full bin, [2] columns that took the generic
  * shared-memory sort, [3] sum of odd-even phases, [4] over-full bins sorted, [5] SM cycles warps
  * spent waiting for a tile, [6] SM cycles of all warps.

@@ -666,3 +666,239 @@ def test_detect_sweep_equals_detect_many_per_probability(method):
             assert h1.columns() == h2.columns()
             assert np.array_equal(h1.array(), h2.array(), equal_nan=True)
     grids.dump()
+
+
+def _station_psets(sts):
+    cols = ['x', 'y', 'time', 'station', 'clim']
+    return [gr.PointSet('c%d' % i, ND, 5, list(cols),
+                        pd.DataFrame(s['obs'], columns=cols))
+            for i, s in enumerate(sts)]
+
+
+@pytest.mark.parametrize('method,kw', [('median', {}), ('mean', {}),
+                                       ('skewness', dict(skewness=0.4)),
+                                       ('percentile', dict(percentile=0.8)),
+                                       ('percentile', dict(percentile=0.95))])
+def test_detect_plan_is_detect_many_without_the_host_round_trips(method, kw):
+    """DetectPlan (station path resident on the device: K2c -> K3 reading the
+    table in place) must return what detect_many returns, and both must equal
+    the oracle."""
+    import torch
+    dims, first, cells = [30, 20, 24], [0.0, 0.0, 1990], [100.0, 100.0, 1]
+    R = 150
+    grids = gr.GridFiles.from_synthetic(1002, R, dims, first, cells, ND)
+    host = synth.stack(1002, R, dims)
+    sts = synth.stations(1002, 9, R, dims, first, cells, tol=1)
+    ref = hmg.detect_many(grids, _station_psets(sts), rad=1, method=method,
+                          prob=0.95, **kw)
+    plan = hmg.DetectPlan(grids, _station_psets(sts), rad=1, method=method,
+                          prob=0.95, **kw)
+    side = torch.cuda.Stream()
+    for _ in range(2):                       # a plan is reusable
+        plan.enqueue(side)
+    got = plan.results()
+    for s, ((h1, d1, m1), (h2, d2, m2)) in enumerate(zip(got, ref)):
+        assert (d1, m1) == (d2, m2)
+        assert h1.columns() == h2.columns()
+        assert np.array_equal(h1.array(), h2.array(), equal_nan=True)
+        df = pd.DataFrame(sts[s]['obs'], columns=['x', 'y', 'time', 'station', 'clim'])
+        ohom, odn, omd = O.detect(host, dims, first, cells, ND, df, ND, rad=1,
+                                  method=method, prob=0.95, **kw)
+        assert (d1, m1) == (odn, omd)
+        assert np.array_equal(h1.values['Flag'].values, ohom['Flag'].values)
+    filled, homog, flagcol, det = plan.fetch()
+    assert filled.shape == (9, dims[2]) and det.shape == (9,)
+    grids.dump()
+
+
+def test_detect_decimal_ties_with_the_percentile_bounds():
+    """the reference compares float64 observations with float64
+    percentiles of float64 realization values, so an observation equal to a
+    bound (both the same decimal, e.g. a DSS clamp value) is INSIDE.  The stack
+    stores float32: the tie must survive.  Realizations clamp to [0.3, 0.7];
+    the observations sit exactly on the clamps."""
+    dims, first, cells = [4, 3, 12], [0.0, 0.0, 2000], [1.0, 1.0, 1]
+    R = 60
+    rng = np.random.default_rng(21)
+    N = int(np.prod(dims))
+    dec = np.clip(np.round(rng.normal(0.5, 0.25, size=(R, N)), 4), 0.3, 0.7)   # float64 decimals
+    grids = gr.GridFiles.from_array(dec.astype(np.float32), dims, first, cells, ND)
+    years = np.arange(2000, 2012)
+    clim = np.where(years % 2 == 0, 0.7, 0.3)
+    clim[5] = 0.7001                       # just outside
+    df = pd.DataFrame({'x': 1.0, 'y': 1.0, 'time': years.astype(float),
+                       'station': 1.0, 'clim': clim})
+    ps = gr.PointSet('tie', ND, 5, list(df.columns), df.copy())
+    hom, dn, md = hmg.detect(grids, ps, method='median', prob=0.95)
+    ohom, odn, omd = O.detect(dec, dims, first, cells, ND, df, ND, method='median',
+                              prob=0.95)
+    assert (dn, md) == (odn, omd)
+    assert dn >= 1                                     # the 0.7001 observation
+    assert np.array_equal(hom.values['Flag'].values, ohom['Flag'].values)
+    grids.dump()
+
+
+def test_detect_series_longer_than_the_grid_raises_like_the_reference():
+    """observations with more rows than the grid has time steps
+    raise ValueError (pandas length mismatch in the reference, homog.py:197)
+    instead of being read past the end of the statistics arrays."""
+    dims, first, cells = [6, 5, 8], [0.0, 0.0, 2000], [1.0, 1.0, 1]
+    grids = gr.GridFiles.from_synthetic(3, 40, dims, first, cells, ND)
+    years = np.arange(2000, 2011)          # 11 rows, dz = 8
+    df = pd.DataFrame({'x': 2.0, 'y': 2.0, 'time': years.astype(float),
+                       'station': 1.0, 'clim': 800.0})
+    cols = list(df.columns)
+    with pytest.raises(ValueError):
+        hmg.detect(grids, gr.PointSet('long', ND, 5, cols, df.copy()), method='mean')
+    with pytest.raises(ValueError):
+        hmg.detect_many(grids, [gr.PointSet('long', ND, 5, cols, df.copy())], method='mean')
+    with pytest.raises(ValueError):
+        _capi.detect(np.zeros((1, 11)), np.zeros((1, 8)), np.zeros((1, 8)),
+                     np.zeros((1, 8)), np.zeros((1, 8)))
+    grids.dump()
+
+
+def test_encoder_matches_printf():
+    """K1's inverse against Python's % formatting: '%12.4f' + CRLF (the DSS map
+    layout, interface/gui.py:1414) and left-justified '%-10.6f' (np.savetxt in
+    GridArr.save, grid.py:341-347), incl. negative, tiny, nan and wide values."""
+    rng = np.random.default_rng(9)
+    vals = np.concatenate([
+        np.round(rng.gamma(2.0, 150.0, size=3000) + 300.0, 4),
+        rng.normal(0, 1, size=3000), rng.normal(0, 1e-5, size=500),
+        [0.0, -0.0, 1.0, -1.0, 0.5, 1e-7, -1e-7, 123456.7, -99999.25, ND, 2.5e-7,
+         0.1234565, 0.0000005, 1234567.125]]).astype(np.float32)
+    rec = _capi.encode_values(vals, 12, 4, crlf=True)
+    got = rec.tobytes().decode()
+    exp = ''.join('%12.4f\r\n' % float(v) for v in vals)
+    assert got == exp
+    v2 = vals.copy()
+    v2[::50] = np.nan
+    rec = _capi.encode_values(v2, 24, 6, left=True)
+    got = [bytes(r[:24]).decode().rstrip(' ') for r in rec]
+    exp = [('%-10.6f' % float(v)).rstrip(' ') for v in v2]
+    assert got == exp
+    assert (rec[:, 24] == 10).all()
+
+
+def test_gridarr_save_on_device_is_savetxt(tmp_path):
+    """GridArr.save of a large float32-valued map goes through the device
+    encoder and must equal np.savetxt(fmt='%-10.6f') byte for byte."""
+    rng = np.random.default_rng(2)
+    val = np.round(rng.gamma(2.0, 150.0, size=70000) + 300.0, 3).astype(np.float32)
+    val[::97] = np.nan
+    val[5] = 12345678.0            # wider than the 10-character field
+    g = gr.GridArr(name='m', dx=70, dy=100, dz=10, val=val.astype(np.float64))
+    out = str(tmp_path / 'map.out')
+    g.save(out, 'meanmap', header=True)
+    ref = str(tmp_path / 'ref.out')
+    with open(ref, 'w') as fid:
+        fid.write('ref\n1\nmeanmap\n')
+        np.savetxt(fid, val.astype(np.float64), fmt='%-10.6f')
+    a, b = open(out, 'rb').read(), open(ref, 'rb').read()
+    assert a.split(b'\n', 1)[1] == b.split(b'\n', 1)[1]
+    # values that are not float32-exact keep the host formatter
+    g2 = gr.GridArr(name='m', dx=7, dy=10, dz=1000, val=rng.normal(size=70000))
+    g2.save(out, 'v', header=False)
+    with open(ref, 'w') as fid:
+        np.savetxt(fid, g2.val, fmt='%-10.6f')
+    assert open(out, 'rb').read() == open(ref, 'rb').read()
+
+
+def test_from_pinned_text_and_pipelined_load(tmp_path):
+    """Config-4 entry points: realization text in pinned host memory ->
+    K1 on rotating streams; and GridFiles.load of fixed-width files through the
+    pinned read ring, node-sharded, with a malformed line reported."""
+    import torch
+    dims, first, cells = [12, 10, 6], [0.0, 0.0, 2000], [1.0, 1.0, 1]
+    R = 9
+    st = synth.stack(33, R, dims)
+    N = st.shape[1]
+    exp = gr.GridFiles.from_array(st, dims, first, cells, ND)
+    ref = exp.stats(lmean=True, lmed=True, lperc=True)
+    n0, n1 = 240, 600                       # layers 2..4
+    texts = []
+    for r in range(R):
+        raw = synth.to_text(st[r, n0:n1], '%12.4f', '\r\n')
+        t = torch.empty(len(raw), dtype=torch.uint8).pin_memory()
+        t.numpy()[:] = np.frombuffer(raw, dtype=np.uint8)
+        texts.append(t)
+    g = gr.GridFiles.from_pinned_text(texts, dims, first, cells, ND, 14, node_range=(n0, n1))
+    got = g._stack.stats_grid(_capi.MEAN | _capi.MEDIAN | _capi.PERC, 0.95, None, ND)
+    assert np.array_equal(got[1].astype(np.float64), ref['medianmap'].val[n0:n1], equal_nan=True)
+    assert np.array_equal(got[2].astype(np.float64), ref['percmap'].val[n0:n1, 0], equal_nan=True)
+    g.dump()
+    # files on disk, sharded load through the read ring
+    firstfile = synth.write_stack(str(tmp_path), 'p_sim', st, '%12.4f', '\r\n', None)
+    g = gr.GridFiles()
+    g.load(firstfile, R, dims, first, cells, ND, 0, node_range=(n0, n1))
+    got = g._stack.stats_grid(_capi.MEDIAN, 0.95, None, ND)
+    assert np.array_equal(got[0].astype(np.float64), ref['medianmap'].val[n0:n1], equal_nan=True)
+    g.dump()
+    # a malformed record inside the range surfaces as ValueError
+    path = os.path.join(str(tmp_path), 'p_sim_4.out')
+    raw = bytearray(open(path, 'rb').read())
+    raw[14 * 300 + 5:14 * 300 + 8] = b'x.y'
+    open(path, 'wb').write(bytes(raw))
+    with pytest.raises(ValueError):
+        gr.GridFiles().load(firstfile, R, dims, first, cells, ND, 0, node_range=(n0, n1))
+    exp.dump()
+
+
+def test_detect_batch_networks_and_probability_sweep():
+    """Config-5 entry point on one rank: every (network, probability, station)
+    result equals the oracle."""
+    dims, first, cells = [16, 12, 10], [0.0, 0.0, 1990], [100.0, 100.0, 1]
+    R = 64
+    probs = [0.9, 0.95, 0.99]
+    nets = []
+    sts = []
+    for i in range(3):
+        s = synth.stations(300 + i, 4, R, dims, first, cells)
+        sts.append(s)
+        nets.append((lambda dev, i=i: gr.GridFiles.from_synthetic(300 + i, R, dims, first,
+                                                                  cells, ND, device=dev),
+                     _station_psets(s)))
+    res = hmg.detect_batch(nets, probs, method='median')
+    assert len(res) == 3
+    for i in range(3):
+        host = synth.stack(300 + i, R, dims)
+        for p in probs:
+            for k, s in enumerate(sts[i]):
+                df = pd.DataFrame(s['obs'], columns=['x', 'y', 'time', 'station', 'clim'])
+                ohom, odn, omd = O.detect(host, dims, first, cells, ND, df, ND,
+                                          method='median', prob=p)
+                hom, dn, md = res[i][p][k]
+                assert (dn, md) == (odn, omd)
+                assert np.array_equal(hom.values['Flag'].values, ohom['Flag'].values)
+
+
+def test_candidate_loop_matches_reference_golden(tmp_path):
+    """launchers.method_classic.gsimcli(skip_dss=True) over pre-existing
+    realization files against the reference's own loop (fixture generated by
+    oracle/make_golden_loop.py through the shim): detections, fills and the
+    final *_homogenised_data.csv."""
+    from gsimcli_b200.launchers import method_classic as mc
+    g = load_golden('candidate_loop')
+    outfolder = str(tmp_path / 'net')
+    os.makedirs(outfolder)
+    for i, st in enumerate(g['stacks']):
+        synth.write_stack(outfolder, 'net_dss_map_st%d_sim' % i, np.array(st), '%12.4f',
+                          '\r\n', None)
+    df = pd.DataFrame(g['stations']['values'], columns=g['stations']['columns'])
+    ps = gr.PointSet('net', g['nodata'], 5, list(df.columns), df)
+    csvfile, dn, fn = mc.gsimcli(ps, True, g['nodata'], g['order'], g['method'], g['prob'],
+                                 True, False, outfolder, True, g['dims'], g['first_coord'],
+                                 g['cells_size'], g['nsim'])
+    assert dn == g['detected'] and fn == g['filled']
+    import io
+    mine = pd.read_csv(csvfile, index_col=0)
+    ref = pd.read_csv(io.StringIO(g['csv']), index_col=0)
+    assert list(mine.columns) == list(ref.columns)
+    assert list(mine.index) == list(ref.index)
+    np.testing.assert_allclose(mine.values.astype(float), ref.values.astype(float),
+                               rtol=1e-12, atol=0)
+    st_mine = pd.read_csv(csvfile.replace('.csv', '_stations.csv'), index_col=0)
+    st_ref = pd.read_csv(io.StringIO(g['stations_csv']), index_col=0)
+    assert st_mine.equals(st_ref)
+    assert not os.path.exists(os.path.join(outfolder, 'net_dss_map_st0_sim.out'))   # purge_sims

@@ -113,3 +113,75 @@ def test_detect_roundtrip_take_candidate_update_station(tmp_path):
     assert np.array_equal(hom.values['Flag'].values, ohom['Flag'].values)
     np.testing.assert_allclose(hom.values['clim'].values, ohom['clim'].values,
                                rtol=5e-13)
+
+
+def _network(seed=4):
+    rng = np.random.default_rng(seed)
+    rows = []
+    for st in (3, 1, 7, 5):
+        for y in range(2000, 2006):
+            v = rng.normal(10 + st, 1 + 0.3 * st)
+            if st == 7 and y == 2002:
+                v = ND
+            rows.append([float(st * 10), float(st * 20), float(y), float(st), v])
+    return pd.DataFrame(rows, columns=['x', 'y', 'time', 'station', 'clim'])
+
+
+def _py2_list_stations(homog):
+    """py2's map() returns a list; station_order / save_output of the reference
+    rely on that (``.sort``, ``len``).  Seventh py2->py3 adaptation, applied to
+    the loaded module only."""
+    orig = homog.list_stations
+    if getattr(orig, '_listed', False):
+        return
+    def listed(*a, **k):
+        return list(orig(*a, **k))
+    listed._listed = True
+    homog.list_stations = listed
+
+
+def test_station_order_matches_reference():
+    from gsimcli_b200.tools import grid as mygr, homog as myhmg
+    _, grid, homog = refshim.load_reference()
+    _py2_list_stations(homog)
+    df = _network()
+    ref_ps = grid.PointSet('net', ND, 5, list(df.columns), df.copy())
+    my_ps = mygr.PointSet('net', ND, 5, list(df.columns), df.copy())
+    for method in ('sorted', 'variance', 'network deviation'):
+        for asc in (True, False):
+            for md_last in (True, False):
+                a = homog.station_order(method, ref_ps, nd=ND, ascending=asc, md_last=md_last)
+                b = myhmg.station_order(method, my_ps, nd=ND, ascending=asc, md_last=md_last)
+                assert list(a) == list(b), (method, asc, md_last)
+    assert myhmg.station_order('user', my_ps, userset=[5, 1]) == \
+        homog.station_order('user', ref_ps, userset=[5, 1])
+    assert sorted(myhmg.station_order('random', my_ps)) == [1, 3, 5, 7]
+    with pytest.raises(TypeError):
+        myhmg.station_order('nonsense', my_ps)
+
+
+def test_save_output_gsimcli_format_matches_reference(tmp_path):
+    from gsimcli_b200.tools import grid as mygr, homog as myhmg
+    _, grid, homog = refshim.load_reference()
+    _py2_list_stations(homog)
+    df = _network()
+    df['Flag'] = ND
+    df.loc[df.index[3], 'Flag'] = df.loc[df.index[3], 'clim']
+    df['median'] = np.nan                      # optional statistic of one station only
+    df.loc[df['station'] == 1.0, 'median'] = 11.25
+    cols = list(df.columns)
+    ref_ps = grid.PointSet('net', ND, len(cols), list(cols), df.copy())
+    my_ps = mygr.PointSet('net', ND, len(cols), list(cols), df.copy())
+    a, b = str(tmp_path / 'ref.csv'), str(tmp_path / 'mine.csv')
+    with warnings.catch_warnings():
+        warnings.simplefilter('ignore')
+        homog.save_output(ref_ps, a, fformat='gsimcli', save_stations=True)
+        myhmg.save_output(my_ps, b, fformat='gsimcli', save_stations=True)
+    ra, rb = pd.read_csv(a, index_col=0), pd.read_csv(b, index_col=0)
+    assert list(ra.columns) == list(rb.columns)
+    assert list(ra.index) == list(rb.index)
+    np.testing.assert_allclose(ra.values.astype(float), rb.values.astype(float),
+                               rtol=0, atol=0, equal_nan=True)
+    sa = pd.read_csv(str(tmp_path / 'ref_stations.csv'), index_col=0)
+    sb = pd.read_csv(str(tmp_path / 'mine_stations.csv'), index_col=0)
+    assert sa.equals(sb)
