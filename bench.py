@@ -429,9 +429,14 @@ def run_cfg3(args):
                           'max_rel_moment': float(np.nanmax(rel)),
                           'max_abs_skew_err': float(np.nanmax(skew_abs)),
                           'moment_mismatches': int((rel > 1e-5).sum() + (~skew_ok).sum())}
-        if bad or parity['grid']['moment_mismatches'] or st_bad or \
-                not parity['stations']['identical_on_all_ranks']:
-            raise RuntimeError('PARITY FAILURE: {0}'.format(json.dumps(parity)))
+        failed = bool(bad or parity['grid']['moment_mismatches'] or st_bad or
+                      not parity['stations']['identical_on_all_ranks'])
+    else:
+        failed = bool(st_bad)
+    # every rank takes part in the verdict (a lone raise would leave the others
+    # waiting in the next collective)
+    if D.max_over_ranks(1.0 if failed else 0.0) > 0:
+        raise RuntimeError('PARITY FAILURE: {0}'.format(json.dumps(parity)))
 
     # ---- e2e: the float32 stack in pinned host memory, maps back to host
     e2e = None
@@ -607,7 +612,11 @@ def run_cfg4(args):
     units = float(RF) * ntotal
     text_bytes = float(RF) * nn * C4_WIDTH
     gbs_rank = D.gather_list(text_bytes * steps / (ms_total * 1e-3) / 1e9)
-    if not ok:
+    h2d_total = int(D.sum_over_ranks(text_bytes))
+    d2h_total = int(D.sum_over_ranks(nplanes * nn * 4))
+    nodes_total = int(D.sum_over_ranks(nn))
+    k1_ms = D.max_over_ranks(k1_ms)
+    if D.max_over_ranks(0.0 if ok else 1.0) > 0:
         raise RuntimeError('PARITY FAILURE: maps from decoded text differ from the '
                            'maps of the stack the text was printed from')
     if rank == 0:
@@ -623,8 +632,8 @@ def run_cfg4(args):
                        'statistics': 'mean, median, skewness, percentile pair (the '
                                      'reference call, grid.py:601-602)'},
             'e2e': {'value': units * steps / (ms_total * 1e-3), 'unit': UNIT,
-                    'h2d_bytes_per_step': int(D.sum_over_ranks(text_bytes)),
-                    'd2h_bytes_per_step': int(D.sum_over_ranks(nplanes * nn * 4)),
+                    'h2d_bytes_per_step': h2d_total,
+                    'd2h_bytes_per_step': d2h_total,
                     'text_gbs_per_rank': [round(x, 2) for x in gbs_rank],
                     'input': 'text in pinned host memory; H2D, K1 decode (3 streams) and '
                              'K2 inside the timed region'},
@@ -635,7 +644,7 @@ def run_cfg4(args):
                          'algorithmic_bytes': k1_alg, 'traffic': None, 'peak_source': peak_src,
                          'k2_kernel_ms': float(np.mean(k_ms))},
             'parity': {'maps_from_text_equal_maps_from_stack': ok, 'planes': nplanes,
-                       'nodes': int(D.sum_over_ranks(nn))},
+                       'nodes': nodes_total},
             'clocks': clocks,
         }
         print(json.dumps(line))

@@ -282,6 +282,8 @@ class GridFiles(object):
         self.node0 = 0          # first grid node held by this stack
         self.sharded = False    # True: this rank holds a node range only
         self._stack = None
+        self._stream_range = None   # only_paths: node range reduced slab by slab
+        self.slab_nodes = None      # only_paths: nodes per slab (None = from free memory)
 
     # ------------------------------------------------------------ lifecycle
     def _geometry(self, dims, first_coord, cells_size, no_data, headerin):
@@ -318,10 +320,71 @@ class GridFiles(object):
     def open_files(self, files_list, dims, first_coord, cells_size, no_data,
                    headerin=3, only_paths=False, device=0, node_range=None):
         """Same with an explicit list of paths (grid.py:509-574).
-        ``only_paths`` is accepted for compatibility: the reference uses it to
-        dodge the OS open-file limit, which does not exist here."""
-        self._open(list(files_list), dims, first_coord, cells_size, no_data,
-                   headerin, device, node_range)
+
+        ``only_paths=True`` (the reference: keep the paths, open nothing,
+        grid.py:564-567) keeps the stack OUT of device memory: ``stats`` then
+        streams the files through the GPU in node slabs -- every slab is the
+        byte range of its nodes in each fixed-width file, decoded (K1), reduced
+        (K2) and dropped -- so a stack larger than HBM can be reduced.  The same
+        path is taken automatically when the stack does not fit."""
+        paths = list(files_list)
+        if not only_paths:
+            self._geometry(dims, first_coord, cells_size, no_data, headerin)
+            n0, n1 = (0, self.cells) if node_range is None else node_range
+            need = len(paths) * (int(n1) - int(n0) + 31) * 4
+            try:
+                import torch
+                free = torch.cuda.mem_get_info(device)[0]
+            except Exception:
+                free = None
+            only_paths = free is not None and need > 0.9 * free
+        if only_paths:
+            for path in paths:
+                if not os.path.isfile(path):
+                    raise IOError('File {0} not found.'.format(path))
+            self._geometry(dims, first_coord, cells_size, no_data, headerin)
+            self.device = device
+            n0, n1 = (0, self.cells) if node_range is None else node_range
+            self.node0 = int(n0)
+            self._stream_range = (int(n0), int(n1))
+            self.sharded = node_range is not None
+            self.dump()
+            self.files = paths
+            self.nfiles = len(paths)
+            return
+        self._open(paths, dims, first_coord, cells_size, no_data, headerin,
+                   device, node_range)
+
+    def _stats_streamed(self, flags, p, percentiles, slab_nodes=None):
+        """``stats`` without a resident stack: node slabs of the files, one
+        after the other (out-of-core form)."""
+        n0, n1 = self._stream_range
+        R = self.nfiles
+        if slab_nodes is None:
+            import torch
+            free = torch.cuda.mem_get_info(self.device)[0]
+            # stack slab + text staging ring: ~ (4 R + 3 * 64) bytes per node
+            slab_nodes = max(32, int(0.5 * free / (4 * R + 192)) // 32 * 32)
+        q = percentiles if percentiles is not None else []
+        nplanes = _capi.lib().gsb_stats_grid_planes(flags, len(q))
+        out = np.empty((nplanes, n1 - n0), dtype=np.float32)
+        save0, savedz = self.node0, self.sharded
+        try:
+            for a in range(n0, n1, slab_nodes):
+                b = min(n1, a + slab_nodes)
+                stack = _capi.Stack(R, b - a, self.device)
+                try:
+                    self.node0 = a
+                    if not self._decode_files_pipelined(stack, self.files):
+                        for r, path in enumerate(self.files):
+                            self._decode_file(stack, r, np.fromfile(path, dtype=np.uint8))
+                    out[:, a - n0:b - n0] = stack.stats_grid(flags, p, percentiles,
+                                                            self.nodata)
+                finally:
+                    stack.close()
+        finally:
+            self.node0, self.sharded = save0, savedz
+        return out
 
     def _open(self, paths, dims, first_coord, cells_size, no_data, headerin,
               device, node_range):
@@ -330,6 +393,7 @@ class GridFiles(object):
         n0, n1 = (0, self.cells) if node_range is None else node_range
         self.node0 = int(n0)
         self.sharded = node_range is not None
+        self._stream_range = None
         self.dump()
         self.files = list(paths)
         self.nfiles = len(paths)
@@ -591,11 +655,15 @@ class GridFiles(object):
         ``modemap``.  Values are float64 arrays widened from the float32 maps
         the kernel writes.
         """
-        stack = self._need_stack()
         sel = dict(lmean=lmean, lmed=lmed, lskew=lskew, lvar=lvar, lstd=lstd,
                    lcoefvar=lcoefvar, lperc=lperc, lmode=lmode)
         flags = _capi.flags_from(**sel)
-        planes = stack.stats_grid(flags, p, percentiles, self.nodata)
+        if self._stack is None and self.nfiles and self.files and \
+                getattr(self, '_stream_range', None) is not None:
+            planes = self._stats_streamed(flags, p, percentiles,
+                                          getattr(self, 'slab_nodes', None))
+        else:
+            planes = self._need_stack().stats_grid(flags, p, percentiles, self.nodata)
         out = {}
         k = 0
         for key, name in _MAP_NAMES:

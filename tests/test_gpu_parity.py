@@ -491,6 +491,15 @@ def test_gridfiles_load_from_files_matches_from_array(tmp_path):
         g2.open_files(list(g.files), dims, first, cells, ND, hdr)
         assert np.array_equal(g2.stats(lmed=True)['medianmap'].val,
                               exp['medianmap'].val, equal_nan=True)
+        # only_paths: the stack never becomes resident, stats() streams node
+        # slabs of the files (out-of-core form); same maps
+        g3 = gr.GridFiles()
+        g3.open_files(list(g.files), dims, first, cells, ND, hdr, only_paths=True)
+        g3.slab_nodes = 96
+        assert g3._stack is None
+        got3 = g3.stats(p=0.9, **sel)
+        for k in exp:
+            assert np.array_equal(got3[k].val, exp[k].val, equal_nan=True), k
         g2.purge()
         assert not os.path.exists(firstfile)
         g.dump()
@@ -902,3 +911,29 @@ def test_candidate_loop_matches_reference_golden(tmp_path):
     st_ref = pd.read_csv(io.StringIO(g['stations_csv']), index_col=0)
     assert st_mine.equals(st_ref)
     assert not os.path.exists(os.path.join(outfolder, 'net_dss_map_st0_sim.out'))   # purge_sims
+
+
+def test_decode_dss_records_fast_path_is_python_float():
+    """The '%12.4f\\r\\n' record parser (SWAR, multiply by 1e-4 guarded against
+    float32 rounding boundaries) must give float32(float(text)) for every
+    spelling the layout allows, incl. exact float32 ties (x.5 between 2^23 and
+    2^24), negative zero, the widest and the smallest values."""
+    rng = np.random.default_rng(123)
+    vals = np.concatenate([
+        np.round(rng.uniform(-999999.0, 9999999.0, size=200000), 4),
+        np.round(rng.gamma(2.0, 150.0, size=100000) + 300.0, 4),
+        np.round(rng.normal(0, 1, size=50000), 4),
+        8388608.0 + np.arange(0, 4000) * 0.5,                 # ties of the float32 grid
+        4194304.0 + np.arange(0, 4000) * 0.25,
+        -(131072.0 + np.arange(0, 4000) * 0.0078125 * 2)[:400],
+        [0.0, -0.0, 0.0001, -0.0001, 9999999.9999, -999999.9999, 1.0, 0.5, 0.1,
+         ND, 16777215.0 / 2, 0.3333, 1e-4 * 12345]])
+    lines = ['%12.4f' % v for v in vals]
+    assert all(len(s) == 12 for s in lines)
+    text = ('\r\n'.join(lines) + '\r\n').encode()
+    stack = _capi.Stack(1, len(lines))
+    stack.decode_text(0, text, 0, 14)
+    got = stack.download()[0]
+    stack.close()
+    exp = _py_float32(lines)
+    assert np.array_equal(got.view(np.int32), exp.view(np.int32))
