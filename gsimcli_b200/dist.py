@@ -29,22 +29,42 @@ def layer_range(dims, rank, world):
     return n0 // per, n1 // per
 
 
-def allgather_tables(local, dims, group=None, device=None):
+def allgather_tables(local, dims, group=None, device=None, zrange=None,
+                     sharded=False):
     """Combine per-rank station tables ``[S][dz][C]`` whose rows are valid only
     for the rank's own time layers into the full table on every rank.
 
-    Each rank contributes the rows of its slab (``layer_range``); ranks may own
+    ``zrange`` = the layers ``(z0, z1)`` this rank's stack really holds (default:
+    ``layer_range(dims, rank, world)``); the ranks' ranges are exchanged and
+    must tile the ``dz`` layers exactly once -- a stack built with another
+    ``node_range`` than ``slab_range`` would otherwise leave NaN rows (and every
+    observation of those layers flagged) without any error.  Ranks may own
     different numbers of layers, so the rows are padded to the largest slab for
-    the fixed-size ``all_gather`` and trimmed afterwards.
+    the fixed-size ``all_gather`` and trimmed afterwards.  ``sharded`` = the
+    caller's stack holds a node range only: then a missing process group is an
+    error, not a single-rank run.
     """
     import torch
     import torch.distributed as td
     if not (td.is_available() and td.is_initialized()):
+        if sharded:
+            raise RuntimeError(
+                'this stack holds a node range only: the station tables of the '
+                'other ranks are needed (torch.distributed is not initialised)')
         return local
     world = td.get_world_size(group)
     rank = td.get_rank(group)
     S, dz, C = local.shape
-    ranges = [layer_range(dims, r, world) for r in range(world)]
+    mine_range = tuple(int(v) for v in (zrange if zrange is not None
+                                        else layer_range(dims, rank, world)))
+    ranges = [None] * world
+    td.all_gather_object(ranges, mine_range, group=group)
+    cover = np.zeros(dz, dtype=np.int64)
+    for a, b in ranges:
+        cover[a:b] += 1
+    if not np.all(cover == 1):
+        raise ValueError("the ranks' time-layer slabs {0} do not tile the {1} "
+                         'layers exactly once'.format(ranges, dz))
     width = max(z1 - z0 for z0, z1 in ranges)
     z0, z1 = ranges[rank]
     mine = np.full((S, width, C), np.nan)

@@ -705,10 +705,13 @@ class GridFiles(object):
     def stats_area_many(self, locs, tol=0, lmean=False, lmed=False,
                         lskew=False, lvar=False, lstd=False, lcoefvar=False,
                         lperc=False, p=0.95, save=False, percentiles=None,
-                        lmode=False, stream=None):
+                        lmode=False, stream=None, local_only=False):
         """Extension: ``stats_area`` for many locations with one kernel
         launch.  Returns a list of ``PointSet``.  ``stream`` is an optional
-        ``cudaStream_t`` handle (int) to enqueue on."""
+        ``cudaStream_t`` handle (int) to enqueue on.  On a node-sharded stack
+        the other ranks' time layers come through the table all-gather
+        (``torch.distributed`` must be initialised); ``local_only=True`` skips
+        the gather and leaves those rows NaN."""
         stack = self._need_stack()
         sel = dict(lmean=lmean, lmed=lmed, lskew=lskew, lvar=lvar, lstd=lstd,
                    lcoefvar=lcoefvar, lperc=lperc, lmode=lmode)
@@ -735,15 +738,22 @@ class GridFiles(object):
             # tables (NCCL over NVLink)
             from .. import dist
             per = self.dx * self.dy
+            if self.node0 % per or (stack.N % per and self.node0 + stack.N
+                                    != per * self.dz):
+                raise ValueError('a node-sharded stack must hold whole time '
+                                 'layers (node range {0}..{1}, {2} nodes per '
+                                 'layer)'.format(self.node0, self.node0 + stack.N, per))
             z0 = self.node0 // per
             z1 = min(self.dz, -(-(self.node0 + stack.N) // per))
             part = stack.stats_columns(np.ascontiguousarray(ids[:, z0:z1]), flags,
                                        p, percentiles, self.nodata, stream)
             table = np.full((len(nodes), self.dz, part.shape[2]), np.nan)
             table[:, z0:z1] = part
-            table = dist.allgather_tables(
-                table, [self.dx, self.dy, self.dz],
-                device='cuda:{0}'.format(self.device))
+            if not local_only:
+                table = dist.allgather_tables(
+                    table, [self.dx, self.dy, self.dz],
+                    device='cuda:{0}'.format(self.device), zrange=(z0, z1),
+                    sharded=True)
         elif len(names) > 3:
             table = stack.stats_columns(ids, flags, p, percentiles, self.nodata,
                                         stream)

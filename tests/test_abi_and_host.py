@@ -229,9 +229,29 @@ local = np.full_like(full, np.nan)
 local[:, z0:z1] = full[:, z0:z1]
 got = dist.allgather_tables(local, dims)
 assert np.array_equal(got, full), (rank, got)
+# the real layer ranges are exchanged: an uneven split the default would not guess
+zr = (0, 1) if rank == 0 else (1, 5)
+local = np.full_like(full, np.nan)
+local[:, zr[0]:zr[1]] = full[:, zr[0]:zr[1]]
+got = dist.allgather_tables(local, dims, zrange=zr, sharded=True)
+assert np.array_equal(got, full), (rank, got)
+# slabs that do not tile the time axis are an error, not NaN rows
+try:
+    dist.allgather_tables(local, dims, zrange=(0, 2) if rank == 0 else (1, 5))
+    raise SystemExit('no error for overlapping slabs')
+except ValueError:
+    pass
 td.destroy_process_group()
 print('ok', rank)
 '''
+
+
+def test_allgather_tables_needs_a_process_group_when_sharded():
+    from gsimcli_b200 import dist
+    local = np.zeros((1, 4, 2))
+    assert dist.allgather_tables(local, [2, 2, 4]) is local          # single process
+    with pytest.raises(RuntimeError):
+        dist.allgather_tables(local, [2, 2, 4], sharded=True)
 
 
 def test_allgather_tables_world2_gloo(tmp_path):

@@ -545,7 +545,10 @@ def test_sharded_stack_reduces_its_own_layers_only():
         part = gr.GridFiles.from_array(st[:, n0:n1], dims, first, cells, ND,
                                        node_range=(n0, n1))
         got = [ps.array() for ps in part.stats_area_many(
-            locs, 1, lmean=True, lmed=True, lperc=True, p=0.9)]
+            locs, 1, lmean=True, lmed=True, lperc=True, p=0.9, local_only=True)]
+        # without a process group the missing layers are an error, not NaN rows
+        with pytest.raises(RuntimeError):
+            part.stats_area_many(locs, 1, lmean=True, lperc=True)
         part.dump()
         for a, b in zip(got, ref):
             assert np.array_equal(a[z0:z1], b[z0:z1])
