@@ -162,9 +162,10 @@ def _oracle_chunk(args):
     dt = time.perf_counter() - t0
     if not keep:
         return dt, None
+    pair = O.grid_stats(cols, ND, O.FLAG_PERC, 0.95)['percmap']        # not timed
     planes = np.vstack([res['meanmap'], res['medianmap'], res['skewmap'], res['varmap'],
                         res['stdmap'], res['coefvarmap'], res['percentiles'].T,
-                        res['modemap']])
+                        res['modemap'], pair.T])
     return dt, planes
 
 
@@ -399,6 +400,22 @@ def run_cfg3(args):
     det_gpu = np.array(res[3], copy=True)
     detected = int(det_gpu.sum())
 
+    # ---- the reference's own call shape, stats(lmean, lmed, lskew, lperc)
+    # (grid.py:601-602): its own kernel instantiation, timed on the K2 stream
+    sflags = _capi.MEAN | _capi.MEDIAN | _capi.SKEW | _capi.PERC
+    snp = _capi.lib().gsb_stats_grid_planes(sflags, 0)
+    d_stock = torch.empty((snp, out_pitch), dtype=torch.float32, device='cuda')
+    stock_ms = []
+    for i in range(4):
+        ev_k0.record(s_grid)
+        stack.stats_grid_device(sflags, 0.95, None, ND, 0, nn, d_stock.data_ptr(),
+                                out_pitch, s_grid.cuda_stream)
+        ev_k1.record(s_grid)
+        ev_k1.synchronize()
+        if i:
+            stock_ms.append(ev_k0.elapsed_time(ev_k1))
+    stock_ms = float(np.mean(stock_ms))
+
     # ---- parity of this very run against the oracle
     parity = {}
     oflags, odet = station_oracle(dims, stations)
@@ -425,6 +442,15 @@ def run_cfg3(args):
             rel = np.abs(got[[0, 3, 4, 5]] - ref[[0, 3, 4, 5]]) / np.abs(ref[[0, 3, 4, 5]])
             skew_abs = np.abs(got[2] - ref[2])
             skew_ok = skew_abs <= 1e-5 + 1e-5 * np.abs(ref[2])
+        sgot = d_stock[:, torch.from_numpy(nodes - n0).cuda()].cpu().numpy().astype(np.float64)
+        sref = ref[[0, 1, 2, nplanes, nplanes + 1]]
+        s32, t32 = sgot[[1, 3, 4]].astype(np.float32), sref[[1, 3, 4]].astype(np.float32)
+        sbad = int((~((s32 == t32) | (np.isnan(s32) & np.isnan(t32)))).sum())
+        with np.errstate(all='ignore'):
+            sbad += int((np.abs(sgot[0] - sref[0]) > 1e-5 * np.abs(sref[0])).sum())
+            sbad += int((np.abs(sgot[2] - sref[2]) > 1e-5 + 1e-5 * np.abs(sref[2])).sum())
+        bad += sbad
+        parity['stock_call'] = {'columns': int(len(nodes)), 'mismatches': sbad}
         parity['grid'] = {'columns': int(len(nodes)), 'order_stat_mismatches': bad,
                           'max_rel_moment': float(np.nanmax(rel)),
                           'max_abs_skew_err': float(np.nanmax(skew_abs)),
@@ -501,13 +527,22 @@ def run_cfg3(args):
                        .format(R * nn * 4 / 1e9),
                        'detected': detected},
             'e2e': e2e,
-            'gpu_launches': 3 * args.steps,
+            'gpu_launches': 3 * args.steps,      # K2, K2c, K3 per step (the 4 stock-call launches are outside the steps)
             'roofline': {'bound': 'hbm', 'achieved': achieved, 'peak': peak,
                          'unit': 'GB/s', 'frac': achieved / peak,
                          'frac_of_nominal_8TBs': achieved / 8000.0,
                          'traffic': measured_traffic(R, nn), 'kernel': 'k2_csort_kernel',
                          'kernel_ms': k_ms, 'kernel_ms_per_rank': [round(x, 3) for x in kms],
                          'algorithmic_bytes': alg_bytes, 'peak_source': peak_src},
+            'stock_call': {
+                'call': 'GridFiles.stats(lmean, lmed, lskew, lperc, p=0.95) -- the '
+                        'reference call shape, grid.py:601-602',
+                'kernel': 'k2_rsel_kernel<16 warps>' if R >= 200 else 'k2_csort_kernel',
+                'kernel_ms': stock_ms,
+                'algorithmic_bytes': 4.0 * R * nn + 4.0 * snp * nn,
+                'achieved': (4.0 * R * nn + 4.0 * snp * nn) / (stock_ms * 1e-3) / 1e9,
+                'frac': (4.0 * R * nn + 4.0 * snp * nn) / (stock_ms * 1e-3) / 1e9 / peak,
+                'unit': 'GB/s'},
             'cpu_baseline': {
                 'value': cpu_val, 'unit': UNIT, 'cores': 1, 'kind': 'port',
                 'host_cores_available': cores,

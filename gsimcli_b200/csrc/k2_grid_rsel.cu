@@ -19,6 +19,11 @@
 // emulation in tests/emul); this file is the tile loop, the barriers and the
 // launcher.  Tiles the kernel cannot finish exactly (flag) are listed in global
 // memory and redone by the counting-sort kernel on the same stream.
+// Production use (k2_grid_sort.cu): the reference's call shape (<= 3 quantile
+// planes, no mode) at R >= 200, where it is 10-20 % faster than the counting
+// sort; with many quantile planes it ties and with the mode plane it is 2.3x
+// slower (lane = column turns per-column decisions into warp divergence), so
+// those stay with the counting sort.  DESIGN.md sections 4 and 8.
 #include "gsb_common.cuh"
 #include "k2_args.cuh"
 #include "k2_rsel_phases.cuh"
@@ -64,15 +69,14 @@ __device__ __forceinline__ float ld_stream_if(const float* p, bool ok) {
 template <int NW, int IPT>
 __device__ __forceinline__ void load_tile(Thr<IPT>& t, const RselLaunch& L, long long tile, int w, int c) {
     const long long col = L.n0 + tile * COLS + c;
-    const float* base = L.data + (col < L.N ? col : L.N - 1);
     const int R = L.a.R;
-    const unsigned pitch = static_cast<unsigned>(L.pitch);
+    const float* p = L.data + (col < L.N ? col : L.N - 1) + static_cast<long long>(w) * L.pitch;
+    const long long step = static_cast<long long>(NW) * L.pitch;      // one row group further
 #pragma unroll
     for (int i = 0; i < IPT; ++i) {
-        const unsigned r = static_cast<unsigned>(i * NW + w);
-        const float* p = base + static_cast<unsigned long long>(r) * pitch;
         if (i < IPT / 2) t.xs[i] = ld_stream(p);
-        else t.xs[i] = ld_stream_if(p, static_cast<int>(r) < R);
+        else t.xs[i] = ld_stream_if(p, i * NW + w < R);
+        p += step;
     }
 }
 
@@ -82,25 +86,24 @@ k2_rsel_kernel(const __grid_constant__ RselLaunch L) {
     constexpr int NT = NW * 32;
     constexpr int S = NW / 8;
     extern __shared__ __align__(16) unsigned char smem_raw[];
+    // fixed-size regions first, at compile-time offsets (their addresses fold
+    // into the instructions); the sort buffer, whose size follows R, is last
+    constexpr int OFF_PART2 = NCELLS * COLS * 4;
+    constexpr int OFF_MODE = OFF_PART2 + 6 * S * COLS * 8;
+    constexpr int OFF_RES = OFF_MODE + COLS * 8;
+    constexpr int OFF_PIVC = OFF_RES + GSB_MAX_PLANES * COLS * 4;
+    constexpr int OFF_INFO = OFF_PIVC + NW * COLS * 4;
+    constexpr int OFF_SORT = (OFF_INFO + CI_WORDS * COLS * 4 + 15) & ~15;
     Smem s;
-    {
-        unsigned char* p = smem_raw;
-        s.sortbuf = reinterpret_cast<float*>(p);
-        s.part = reinterpret_cast<uint32_t*>(p);
-        s.chunk = reinterpret_cast<uint32_t*>(p);
-        p += static_cast<size_t>(L.sort_words) * 4;
-        s.cells = reinterpret_cast<uint32_t*>(p);
-        p += NCELLS * COLS * 4;
-        s.part2 = reinterpret_cast<double*>(p);
-        p += 6 * S * COLS * 8;
-        s.modekey = reinterpret_cast<unsigned long long*>(p);
-        p += COLS * 8;
-        s.res = reinterpret_cast<float*>(p);
-        p += GSB_MAX_PLANES * COLS * 4;
-        s.pivc = reinterpret_cast<float*>(p);
-        p += NW * COLS * 4;
-        s.colinfo = reinterpret_cast<uint32_t*>(p);
-    }
+    s.cells = reinterpret_cast<uint32_t*>(smem_raw);
+    s.part2 = reinterpret_cast<double*>(smem_raw + OFF_PART2);
+    s.modekey = reinterpret_cast<unsigned long long*>(smem_raw + OFF_MODE);
+    s.res = reinterpret_cast<float*>(smem_raw + OFF_RES);
+    s.pivc = reinterpret_cast<float*>(smem_raw + OFF_PIVC);
+    s.colinfo = reinterpret_cast<uint32_t*>(smem_raw + OFF_INFO);
+    s.sortbuf = reinterpret_cast<float*>(smem_raw + OFF_SORT);
+    s.part = reinterpret_cast<uint32_t*>(smem_raw + OFF_SORT);
+    s.chunk = reinterpret_cast<uint32_t*>(smem_raw + OFF_SORT);
     const int tid = threadIdx.x;
     const int w = tid >> 5, c = tid & 31;
     const Args& a = L.a;
@@ -169,8 +172,9 @@ size_t rsel_smem(int R, int* sort_words) {
     const int need_alias = 6 * NW * COLS;       // `part` is the largest alias
     const int words = ((need_rows > need_alias ? need_rows : need_alias) + 3) & ~3;
     *sort_words = words;
-    return static_cast<size_t>(words) * 4 + NCELLS * COLS * 4 + 6 * (NW / 8) * COLS * 8 + COLS * 8 +
-           GSB_MAX_PLANES * COLS * 4 + NW * COLS * 4 + CI_WORDS * COLS * 4;
+    const size_t fixed = (static_cast<size_t>(NCELLS) * COLS * 4 + 6 * (NW / 8) * COLS * 8 + COLS * 8 +
+                          GSB_MAX_PLANES * COLS * 4 + NW * COLS * 4 + CI_WORDS * COLS * 4 + 15) & ~size_t(15);
+    return fixed + static_cast<size_t>(words) * 4;
 }
 
 template <int NW, int IPT, bool MODE>

@@ -608,21 +608,30 @@ int gsb_launch_k2_sort(gsb_stack* s, const GsbPlanes& pl, float nodata, int64_t 
     const int ctas = s->sm_count - s->k2_sm_reserve;
     const int grid = static_cast<int>(args.ntiles < ctas ? args.ntiles : ctas);
     if (grid <= 0) return GSB_OK;
-    // R > 32: the counting-sort kernel (k2_grid_csort.cu).  R <= 32: the register
-    // bitonic sort below.  `k2_algo` (gsb_stack_set_option, tests and profiling
-    // only) selects another of the three implementations so that the parity
-    // suite can cross-check them: 2 = bitonic for every R, 3 = the register-tile
-    // kernel (k2_grid_rsel.cu: measured equal to the counting sort without the
-    // mode plane and 2.3x slower with it -- DESIGN.md section 8), whose flagged
-    // tiles (bin map collapsed by an outlier, heavy ties, range overflow) are
-    // redone by the counting-sort kernel on the same stream.
+    // R > 32: the counting-sort kernel (k2_grid_csort.cu) -- except the
+    // reference's own call shape (grid.py:601-602: moments + median + one
+    // percentile pair, i.e. at most 3 quantile planes and no mode) on deep
+    // columns, where the register-tile kernel (k2_grid_rsel.cu, 16 warps) is
+    // 10-20 % faster (R = 200 / 500 / 1000: 4.70 / 3.06 / 3.18 ms against 5.30 /
+    // 3.90 / 3.69 ms per 4 GB of stack, profiles/r02_k2_stock_call_timing.log);
+    // with more quantile planes or the mode it is not.
+    // R <= 32: the register bitonic sort below.  `k2_algo`
+    // (gsb_stack_set_option, tests and profiling only) forces one of the three
+    // implementations so that the parity suite can cross-check them: 1 =
+    // counting sort, 2 = bitonic for every R, 3 = register tile.  Tiles the
+    // register-tile kernel flags (bin map collapsed by an outlier, heavy ties,
+    // range overflow) are redone by the counting-sort kernel on the same stream.
+    int nquant = 0;
+    for (int i = 0; i < pl.n; ++i) nquant += pl.kind[i] == GSB_PK_QUANT ? 1 : 0;
+    const bool stock_call = !pl.need_mode && nquant <= 3 && s->R >= 200;
     const int algo = s->k2_algo;
     if (ipt >= 2 && algo != 2) {
-        if (algo != 3)
+        if (algo == 1 || (algo == 0 && !stock_call))
             return gsb_launch_k2_csort(s, args, ipt, grid, pl.need_mode != 0, 10, st);
+        const int nw = algo == 3 ? (s->k2_nw == 16 ? 16 : 32) : 16;
         int* d_flagged = s->k2_flags;        // ntiles <= pitch / 32 + 1 (unaligned n0)
         GSB_CUDA(cudaMemsetAsync(d_flagged, 0, sizeof(int), st));
-        int rc = gsb_launch_k2_rsel(s, args, grid, pl.need_mode != 0, s->k2_nw == 16 ? 16 : 32, d_flagged, st);
+        int rc = gsb_launch_k2_rsel(s, args, grid, pl.need_mode != 0, nw, d_flagged, st);
         if (rc) return rc;
         args.tile_list = d_flagged;
         return gsb_launch_k2_csort(s, args, ipt, grid, pl.need_mode != 0, 10, st);

@@ -21,7 +21,7 @@ stack = _capi.Stack(R, N)
 stack.synth_fill(1003, dims, NODE0, -999.9)
 # test-only kernel selection: register tile (32 / 16 warps), counting sort, bitonic
 ALGO = os.environ.get('GSB_PROF_ALGO', 'csort')
-k2_algo, k2_nw = {'rsel': (3, 0), 'rsel16': (3, 16), 'csort': (0, 0), 'bitonic': (2, 0)}[ALGO]
+k2_algo, k2_nw = {'rsel': (3, 0), 'rsel16': (3, 16), 'csort': (1, 0), 'bitonic': (2, 0)}[ALGO]
 stack.set_option('k2_algo', k2_algo)
 stack.set_option('k2_nw', k2_nw)
 if os.environ.get('GSB_K2_STATS'):

@@ -17,8 +17,8 @@ npl = _capi.lib().gsb_stats_grid_planes(flags, len(QS))
 out = torch.empty((npl, N), dtype=torch.float32, device='cuda')
 st = torch.cuda.current_stream().cuda_stream
 res = {}
-for algo in ('csort', 'bitonic'):
-    os.environ['GSB_K2_ALGO'] = algo
+for algo, code in (('csort', 1), ('bitonic', 2), ('rsel', 3)):
+    stack.set_option('k2_algo', code)       # test-only kernel selection
     e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
     for i in range(3):
         e0.record(); stack.stats_grid_device(flags, 0.95, QS, -999.9, 0, N, out.data_ptr(), N, st); e1.record()
@@ -27,4 +27,5 @@ for algo in ('csort', 'bitonic'):
     res[algo] = out[1:].clone()     # all planes but the mean (moments differ in the last bits)
 q = slice(5, None)
 assert torch.equal(res['csort'][q].view(torch.int32), res['bitonic'][q].view(torch.int32)), 'order statistics differ'
+assert torch.equal(res['rsel'][q].view(torch.int32), res['bitonic'][q].view(torch.int32)), 'order statistics differ (rsel)'
 print('order statistics and mode identical')

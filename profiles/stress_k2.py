@@ -43,7 +43,7 @@ for it in range(rounds):
     stack.upload(st32)
     outs = {}
     pp = float(rng.choice([0.9, 0.95, 0.5]))
-    for algo, (k2_algo, k2_nw) in (('rsel', (3, 0)), ('rsel16', (3, 16)), ('csort', (0, 0)), ('bitonic', (2, 0))):
+    for algo, (k2_algo, k2_nw) in (('rsel', (3, 0)), ('rsel16', (3, 16)), ('csort', (1, 0)), ('bitonic', (2, 0))):
         stack.set_option('k2_algo', k2_algo)
         stack.set_option('k2_nw', k2_nw)
         outs[algo] = stack.stats_grid(flags, pp, qs, ND)

@@ -265,3 +265,13 @@ def test_allgather_tables_world2_gloo(tmp_path):
     for p, o in zip(procs, outs):
         assert p.returncode == 0, o
         assert 'ok' in o
+
+
+def test_library_reads_no_environment_switches():
+    """VERDICT r1: kernel selection must not hang off getenv in product code;
+    the test-only knobs are stack options (gsb_stack_set_option)."""
+    csrc = os.path.join(ROOT, 'gsimcli_b200', 'csrc')
+    for name in os.listdir(csrc):
+        if name.endswith(('.cu', '.cuh')):
+            with open(os.path.join(csrc, name)) as fh:
+                assert 'getenv' not in fh.read(), name

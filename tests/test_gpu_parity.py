@@ -47,7 +47,7 @@ def close(a, b, rtol=1e-5, atol=0.0):
 
 # the three full-grid K2 kernels, forced through the test-only stack options:
 # register tile (default; 32 or 16 warps), counting sort, register bitonic sort
-ALGOS = {'rsel': (3, 0), 'rsel16': (3, 16), 'csort': (0, 0), 'bitonic': (2, 0)}
+ALGOS = {'rsel': (3, 0), 'rsel16': (3, 16), 'csort': (1, 0), 'bitonic': (2, 0)}
 
 
 def force_algo(stack, algo):
