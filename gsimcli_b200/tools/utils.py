@@ -1,12 +1,8 @@
 # -*- coding: utf-8 -*-
-"""The two helpers of ``GSIMCLI/tools/utils.py`` the hot path depends on."""
+"""The helper of ``GSIMCLI/tools/utils.py`` the hot path depends on.
+(``skip_lines``, utils.py:66-78, has no counterpart: header lines are skipped by
+the K1 decoder, ``gsb_decode_text(header_lines=...)``.)"""
 import os
-
-
-def skip_lines(file_id, nlines):
-    """Advance a file object by ``nlines`` lines (utils.py:66-78)."""
-    for _ in range(nlines):
-        file_id.readline()
 
 
 def filename_indexing(file_id, n):
