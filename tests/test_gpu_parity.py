@@ -940,3 +940,28 @@ def test_decode_dss_records_fast_path_is_python_float():
     stack.close()
     exp = _py_float32(lines)
     assert np.array_equal(got.view(np.int32), exp.view(np.int32))
+
+
+@pytest.mark.parametrize('R', [200, 333, 1000])
+def test_stock_call_shape_default_dispatch_subranges(R):
+    """The reference's call shape (moments + median + percentile pair, no mode)
+    at R >= 200 takes the register-tile kernel by default: unaligned node
+    sub-ranges, ranges ending inside a tile, a flagged tile (outlier column)
+    handed to the counting sort, and the slab-pipelined host path."""
+    import torch
+    st = synth.stack(90 + R, R, [23, 9, 5])          # N = 1035: not a multiple of 32
+    st[0, 100] = 3.0e6                               # bin map collapses in that tile -> fallback
+    st[:, 200] = np.float32(ND)
+    for n0, nn in ((0, None), (37, 401), (64, 64), (5, 1030)):
+        check_grid(st, p=0.9, percentiles=None, mode=False, n0=n0, nn=nn)
+    N = st.shape[1]
+    stack = _capi.Stack(R, N)
+    stack.upload(st)
+    res = stack.stats_grid(ALLF, 0.95, None, ND)
+    assert stack.k2_flagged() >= 1                   # the outlier tile went to the counting sort
+    host = torch.from_numpy(np.ascontiguousarray(st)).pin_memory()
+    maps = torch.empty((res.shape[0], N), dtype=torch.float32).pin_memory()
+    stack.stats_grid_from_host(host.data_ptr(), N, ALLF, 0.95, None, ND, maps, nslabs=3)
+    torch.cuda.synchronize()
+    assert np.array_equal(maps.numpy().view(np.int32), res.view(np.int32))
+    stack.close()
