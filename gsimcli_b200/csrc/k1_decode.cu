@@ -16,6 +16,7 @@
 //   * general: a newline index is built on the device (16 bytes per thread,
 //     byte-compare masks, block scan of popcounts), then one thread per line.
 #include "gsb_common.cuh"
+#include "k1_dss14.cuh"
 
 namespace {
 
@@ -240,73 +241,17 @@ __device__ __forceinline__ bool parse_fixed_fast(const unsigned char* p, int W, 
     return true;
 }
 
-// ---- the DSS map record itself: '%12.4f\r\n' (interface/gui.py:1414) ------------
-// 14 bytes: blanks, an optional '-', the integer digits right-aligned in bytes
-// 0..6, '.' at byte 7, four fraction digits, CR, LF.  Everything is done on four
-// 32-bit words: SWAR byte classes (digit / blank / minus) validate the layout,
-// each word of digits becomes a number with two multiply-adds (blanks count as
-// leading zeros), and the decimal -> float64 division by 10^4 is a multiply by
-// the rounded reciprocal, accepted only when the float64 result is provably far
-// enough from a float32 rounding boundary for the final float32 to equal the
-// correctly rounded path (otherwise, and for any other layout, the caller
-// falls through to the general parsers).  Same value, bit for bit.
-__device__ __forceinline__ unsigned k1_notdigit(unsigned u) {      // 0x80 per non-digit byte
-    const unsigned t = u ^ 0x30303030u;
-    return (((t & 0x7f7f7f7fu) + 0x76767676u) | t) & 0x80808080u;
-}
-__device__ __forceinline__ unsigned k1_nonzero(unsigned z) {       // 0x80 per non-zero byte
-    return (((z & 0x7f7f7f7fu) + 0x7f7f7f7fu) | z) & 0x80808080u;
-}
-__device__ __forceinline__ unsigned k1_digits4(unsigned t) {       // 4 digit bytes (byte 0 first) -> number
-    t = (t * 10u + (t >> 8)) & 0x00ff00ffu;
-    return (t * 100u + (t >> 16)) & 0xffffu;
-}
-
+// ---- the DSS map record itself: '%12.4f\r\n' (interface/gui.py:1414): k1_dss14.cuh
 __device__ __forceinline__ bool parse_dss14(const unsigned char* p, float* out) {
     const unsigned addr = static_cast<unsigned>(reinterpret_cast<uintptr_t>(p));
     const unsigned sh = (addr & 3u) * 8u;
     const unsigned* wp = reinterpret_cast<const unsigned*>(p - (addr & 3u));
     const unsigned a0 = wp[0], a1 = wp[1], a2 = wp[2], a3 = wp[3], a4 = wp[4];
-    const unsigned u0 = __funnelshift_r(a0, a1, sh);     // bytes 0..3   integer part
-    const unsigned u1 = __funnelshift_r(a1, a2, sh);     // bytes 4..7   integer part, '.'
-    const unsigned u2 = __funnelshift_r(a2, a3, sh);     // bytes 8..11  fraction
-    const unsigned u3 = __funnelshift_r(a3, a4, sh);     // bytes 12..13 CR LF
-    // fixed characters
-    bool ok = ((u1 >> 24) == 0x2eu) && ((u3 & 0xffffu) == 0x0a0du);
-    // byte classes of the 7 integer-part bytes
-    const unsigned nd0 = k1_notdigit(u0), nd1 = k1_notdigit(u1);
-    const unsigned D0 = nd0 ^ 0x80808080u, D1 = (nd1 ^ 0x80808080u) & 0x00808080u;
-    const unsigned M0 = k1_nonzero(u0 ^ 0x2d2d2d2du) ^ 0x80808080u;
-    const unsigned M1 = (k1_nonzero(u1 ^ 0x2d2d2d2du) ^ 0x80808080u) & 0x00808080u;
-    const unsigned S0 = k1_nonzero(u0 ^ 0x20202020u) ^ 0x80808080u;
-    const unsigned S1 = (k1_nonzero(u1 ^ 0x20202020u) ^ 0x80808080u) & 0x00808080u;
-    ok = ok && ((D0 | M0 | S0) == 0x80808080u) && ((D1 | M1 | S1) == 0x00808080u);
-    ok = ok && (D1 & 0x00800000u);                        // byte 6 is a digit
-    // digits form a suffix of bytes 0..6 (no non-digit after a digit) and a '-'
-    // is followed by a digit: with both, the layout is blanks* '-'? digits+
-    const unsigned long long D = (static_cast<unsigned long long>(D1) << 32) | D0;
-    const unsigned long long M = (static_cast<unsigned long long>(M1) << 32) | M0;
-    const unsigned long long in7 = 0x0080808080808080ull;
-    ok = ok && ((((D << 8) & ~D) & in7) == 0ull) && ((((M << 8) & ~D) & (in7 | (1ull << 63))) == 0ull);
-    ok = ok && (k1_notdigit(u2) == 0u);
-    if (!ok) return false;
-    // digit bytes keep their low nibble, everything else (blank, '-') is zero
-    const unsigned v0 = k1_digits4(u0 & ((D0 >> 7) * 0x0fu));
-    const unsigned v1 = k1_digits4(u1 & ((D1 >> 7) * 0x0fu));    // d4 d5 d6 0 = 10 * (d4 d5 d6)
-    const unsigned v2 = k1_digits4(u2 & 0x0f0f0f0fu);
-    const unsigned ip10 = v0 * 10000u + v1;                      // 10 * integer part < 10^8
-    // m = integer * 10^4 + fraction, exact in float64 (< 10^11)
-    const double m = fma(static_cast<double>(ip10), 1000.0, static_cast<double>(v2));
-    double x = __dmul_rn(m, 1.0e-4);
-    // x is within 2^-51 (relative) of the correctly rounded m / 10^4.  The
-    // float32 rounding boundaries of a float64 are the values whose low 29
-    // mantissa bits are 0x10000000: stay 16 units away from them (and from the
-    // wrap of the bits below, 0 and 2^29) or take the exact division.
-    const unsigned low = static_cast<unsigned>(__double2loint(x)) & 0x1fffffffu;
-    if (((low + 16u) & 0x0fffffffu) < 32u) x = __ddiv_rn(m, 1.0e4);
-    if (M != 0ull) x = -x;
-    *out = __double2float_rn(x);
-    return true;
+    return k1_parse_dss14_words(__funnelshift_r(a0, a1, sh),      // bytes 0..3   integer part
+                                __funnelshift_r(a1, a2, sh),      // bytes 4..7   integer part, '.'
+                                __funnelshift_r(a2, a3, sh),      // bytes 8..11  fraction
+                                __funnelshift_r(a3, a4, sh),      // bytes 12..13 CR LF
+                                out);
 }
 
 __global__ void __launch_bounds__(K1_THREADS)

@@ -18,3 +18,18 @@ def build(force=False):
     subprocess.run(['g++', '-O2', '-std=c++17', '-ffp-contract=off', '-Wno-unknown-pragmas',
                     '-shared', '-fPIC', '-o', LIB, SRC], check=True)
     return LIB
+
+
+K1_SRC = os.path.join(HERE, 'k1_dss14_emul.cpp')
+K1_HDR = os.path.join(HERE, '..', '..', 'gsimcli_b200', 'csrc', 'k1_dss14.cuh')
+K1_LIB = os.path.join(HERE, 'libk1dss14_emul.so')
+
+
+def build_k1(force=False):
+    """The K1 '%12.4f CRLF' record parser (csrc/k1_dss14.cuh) for the host."""
+    if (not force and os.path.exists(K1_LIB)
+            and os.path.getmtime(K1_LIB) >= max(os.path.getmtime(K1_SRC), os.path.getmtime(K1_HDR))):
+        return K1_LIB
+    subprocess.run(['g++', '-O2', '-std=c++17', '-ffp-contract=off', '-shared', '-fPIC',
+                    '-o', K1_LIB, K1_SRC], check=True)
+    return K1_LIB
