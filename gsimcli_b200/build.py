@@ -16,7 +16,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, 'csrc')
 OBJ = os.path.join(HERE, 'csrc', 'build')
 LIB = os.path.join(HERE, 'libgsimcli_b200.so')
-SOURCES = ['gsb_capi.cu', 'k1_decode.cu', 'k2_grid_sort.cu', 'k2_grid_csort.cu', 'k2_grid_rsel.cu', 'k2_moments.cu',
+SOURCES = ['gsb_capi.cu', 'k1_decode.cu', 'k2_grid_sort.cu', 'k2_grid_csort.cu', 'k2_grid_rsel.cu', 'k2_grid_ssel.cu', 'k2_moments.cu',
            'k2_columns.cu', 'gsb_synth.cu']
 NVCC = os.environ.get('NVCC', '/usr/local/cuda/bin/nvcc')
 FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-O3', '-std=c++17',

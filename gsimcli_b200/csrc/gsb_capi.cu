@@ -218,7 +218,7 @@ int gsb_stack_set_option(gsb_stack* s, const char* key, int64_t value) {
         return GSB_OK;
     }
     if (strcmp(key, "k2_algo") == 0) {
-        GSB_REQUIRE(value >= 0 && value <= 3, "k2_algo must be 0..3");
+        GSB_REQUIRE(value >= 0 && value <= 4, "k2_algo must be 0..4");
         s->k2_algo = (int)value;
         return GSB_OK;
     }

@@ -54,7 +54,7 @@ struct gsb_stack {
                            // gsb_k2_box_rows(R) rows, 128B swizzle, OOB -> NaN
     int tmap_ok;
     int k2_sm_reserve;     // SMs the K2 grid leaves free (gsb_stack_set_option)
-    int k2_algo;           // tests only: 0 = default, 1 = counting sort, 2 = bitonic, 3 = register tile
+    int k2_algo;           // tests only: 0 = default, 1 = counting sort, 2 = bitonic, 3 = register tile, 4 = staged select
     int k2_nw;             // tests only: warps per CTA of the register-tile kernel (0 = default)
     int k2_stats;          // diagnostic counters of the counting-sort kernel
     int* k2_flags;         // device, [0] count + one slot per 32-node tile: tiles the register-

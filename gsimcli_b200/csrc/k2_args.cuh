@@ -35,3 +35,8 @@ int gsb_launch_k2_csort(gsb_stack* s, const K2Args& args, int ipt, int grid, boo
 // appended to d_flagged ([0] count, [1 + k] tile) for the counting-sort kernel
 int gsb_launch_k2_rsel(gsb_stack* s, const K2Args& args, int grid, bool mode, int nw,
                        int* d_flagged, cudaStream_t st);
+// staged-select kernel (k2_grid_ssel.cu, experimental, k2_algo = 4): the reference's call
+// shape only (gsb_k2_ssel_supports); flagged tiles as for the register-tile kernel
+bool gsb_k2_ssel_supports(const K2Args& args, bool mode);
+int gsb_launch_k2_ssel(gsb_stack* s, const K2Args& args, int grid, bool mode, int nw,
+                       int* d_flagged, cudaStream_t st);

@@ -631,7 +631,11 @@ int gsb_launch_k2_sort(gsb_stack* s, const GsbPlanes& pl, float nodata, int64_t 
         const int nw = algo == 3 ? (s->k2_nw == 16 ? 16 : 32) : 16;
         int* d_flagged = s->k2_flags;        // ntiles <= pitch / 32 + 1 (unaligned n0)
         GSB_CUDA(cudaMemsetAsync(d_flagged, 0, sizeof(int), st));
-        int rc = gsb_launch_k2_rsel(s, args, grid, pl.need_mode != 0, nw, d_flagged, st);
+        // 4 = the staged-select kernel (k2_grid_ssel.cu): experimental, never the
+        // default; shapes it does not serve fall to the register-tile kernel
+        const bool ssel = algo == 4 && gsb_k2_ssel_supports(args, pl.need_mode != 0);
+        int rc = ssel ? gsb_launch_k2_ssel(s, args, grid, false, s->k2_nw == 32 ? 32 : 16, d_flagged, st)
+                      : gsb_launch_k2_rsel(s, args, grid, pl.need_mode != 0, nw, d_flagged, st);
         if (rc) return rc;
         args.tile_list = d_flagged;
         return gsb_launch_k2_csort(s, args, ipt, grid, pl.need_mode != 0, 10, st);

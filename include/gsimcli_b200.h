@@ -99,8 +99,10 @@ int gsb_stack_info(const gsb_stack* s, int64_t* R, int64_t* N, int64_t* pitch,
  * free (default 0) so that station-column / detect launches on another stream
  * run concurrently with it instead of queueing behind its persistent CTAs.
  * Tests and profiling only: "k2_algo" selects the full-grid kernel (0 = default,
- * 1 = counting sort, 2 = register bitonic for every R, 3 = register tile), "k2_nw" the warps per
- * CTA of the register-tile kernel, "k2_stats" enables gsb_debug_cs_counters. */
+ * 1 = counting sort, 2 = register bitonic for every R, 3 = register tile, 4 = the
+ * experimental staged-select kernel for the reference's call shape -- other shapes
+ * take the register tile), "k2_nw" the warps per CTA of the register-tile /
+ * staged-select kernel, "k2_stats" enables gsb_debug_cs_counters. */
 int gsb_stack_set_option(gsb_stack* s, const char* key, int64_t value);
 /* diagnostic: number of 32-node tiles of the last gsb_stats_grid call on this
  * stack that the register-tile kernel handed to the counting-sort kernel

@@ -33,3 +33,23 @@ def build_k1(force=False):
     subprocess.run(['g++', '-O2', '-std=c++17', '-ffp-contract=off', '-shared', '-fPIC',
                     '-o', K1_LIB, K1_SRC], check=True)
     return K1_LIB
+
+
+SSEL_SRC = os.path.join(HERE, 'k2_ssel_emul.cpp')
+SSEL_HDR = os.path.join(HERE, '..', '..', 'gsimcli_b200', 'csrc', 'k2_ssel_phases.cuh')
+SSEL_LIB = os.path.join(HERE, 'libk2ssel_emul.so')
+
+
+def build_ssel(force=False, sanitize=False):
+    """The staged-select K2 kernel's phases (csrc/k2_ssel_phases.cuh, which
+    includes k2_rsel_phases.cuh) for the host.  ``sanitize`` builds an
+    AddressSanitizer + UBSan variant next to it (run in a subprocess with
+    libasan preloaded)."""
+    lib = SSEL_LIB.replace('.so', '_asan.so') if sanitize else SSEL_LIB
+    newest = max(os.path.getmtime(SSEL_SRC), os.path.getmtime(SSEL_HDR), os.path.getmtime(HDR))
+    if not force and os.path.exists(lib) and os.path.getmtime(lib) >= newest:
+        return lib
+    flags = ['-O1', '-g', '-fsanitize=address,undefined', '-fno-omit-frame-pointer'] if sanitize else ['-O2']
+    subprocess.run(['g++'] + flags + ['-std=c++17', '-ffp-contract=off', '-Wno-unknown-pragmas',
+                    '-shared', '-fPIC', '-o', lib, SSEL_SRC], check=True)
+    return lib
