@@ -29,6 +29,12 @@ pinned HOST buffers (H2D of the inputs and D2H of the results inside the timed
 region); ``roofline`` for the dominant kernel against the measured HBM peak;
 ``cpu_baseline`` = the NumPy oracle on a bounded sample on the host cores;
 ``parity`` = the GPU results of this very run checked against the oracle.
+``experimental`` (default run, one GPU): measurements taken in a SUBPROCESS
+(``--leg extras``: own CUDA context, hard time limit, cannot disturb the line) of
+code that was written after the round's GPU budget was spent -- the opt-in
+staged-select K2 kernel on the reference's call shape, checked bit for bit
+against the default kernel, and K1 on resident text larger than L2; each part
+reports its own ``error`` instead of failing the run.
 """
 import argparse
 import json
@@ -508,6 +514,12 @@ def run_cfg3(args):
     except (RuntimeError, MemoryError) as exc:     # e.g. cannot pin 16 GB
         e2e = {'value': None, 'unit': UNIT, 'error': str(exc)[:200]}
     clocks = sampler.finish()
+    # code that has never run on a GPU at commit time is measured in a subprocess
+    # (own context, hard time limit) after everything the line reports is done
+    extras = None
+    if world == 1 and not fast and os.environ.get('GSB_BENCH_EXTRAS', '1') != '0':
+        torch.cuda.synchronize()
+        extras = extras_subprocess()
 
     kms = D.gather_list(float(np.mean(kernel_ms)))
     if rank == 0:
@@ -552,9 +564,147 @@ def run_cfg3(args):
             'parity': parity,
             'clocks': clocks,
         }
+        if extras is not None:
+            line['experimental'] = extras
         print(json.dumps(line))
     grids.dump()
     D.close()
+
+
+# ------------------------------------------------------------------ extras
+def run_extras(args):
+    """``--leg extras`` (a SUBPROCESS of the default run, own CUDA context, so
+    that nothing here can disturb the benchmark line): measurements of code that
+    was written after this round's GPU budget was spent and has never run on a
+    device at commit time.
+
+    * the experimental staged-select K2 kernel (csrc/k2_grid_ssel.cu, stack
+      option k2_algo = 4) on the reference's call shape, 16 and 32 warps, 10^6
+      columns of the benchmark stack, checked against the default kernel's maps
+      (bit for bit) and the oracle;
+    * K1 on resident text larger than L2 (16 x 10^6 DSS records = 224 MB).
+    Prints one JSON object; every part carries its own ``error`` on failure."""
+    import torch
+    from gsimcli_b200 import _capi, synth
+    from gsimcli_b200.tools import grid as gr
+    from oracle import np_oracle as O
+    out = {}
+    dims = [DIMS1[0], DIMS1[1], 25]
+    nn = int(np.prod(dims))
+    peak, _ = peaks()
+    L = _capi.lib()
+    grids = gr.GridFiles.from_synthetic(SEED, R, dims, FIRST, CELLS, ND, device=0)
+    stack = grids._stack
+    sflags = _capi.MEAN | _capi.MEDIAN | _capi.SKEW | _capi.PERC
+    snp = L.gsb_stats_grid_planes(sflags, 0)
+    alg = 4.0 * R * nn + 4.0 * snp * nn
+    e0 = torch.cuda.Event(enable_timing=True)
+    e1 = torch.cuda.Event(enable_timing=True)
+
+    def timed(d_maps, reps=4):
+        ms = []
+        for i in range(reps):
+            e0.record()
+            stack.stats_grid_device(sflags, 0.95, None, ND, 0, nn, d_maps.data_ptr(), nn, None)
+            e1.record()
+            e1.synchronize()
+            if i:
+                ms.append(e0.elapsed_time(e1))
+        return float(np.mean(ms))
+
+    try:
+        d_ref = torch.empty((snp, nn), dtype=torch.float32, device='cuda')
+        ref_ms = timed(d_ref)
+        ss = {'workload': '{0} realizations x {1} columns, stats(lmean, lmed, lskew, lperc)'.format(R, nn),
+              'default_kernel_ms': ref_ms, 'default_frac': alg / (ref_ms * 1e-3) / 1e9 / peak,
+              'algorithmic_bytes': alg}
+        nodes = sample_nodes(dims, 4096)
+        host = synth.columns(SEED, R, dims, nodes)
+        oref = O.grid_stats(host, ND, O.FLAG_MEAN | O.FLAG_MED | O.FLAG_SKEW | O.FLAG_PERC, 0.95, None)
+        oexact = np.stack([oref['medianmap'], oref['percmap'][:, 0], oref['percmap'][:, 1]]).astype(np.float32)
+        idx = torch.from_numpy(nodes).cuda()
+        for nw in (16, 32):
+            key = 'nw%d' % nw
+            try:
+                stack.set_option('k2_algo', 4)
+                stack.set_option('k2_nw', nw)
+                d_new = torch.full((snp, nn), -7.0, dtype=torch.float32, device='cuda')
+                ms = timed(d_new)
+                flagged = stack.k2_flagged()
+                a, b = d_new.view(torch.int32), d_ref.view(torch.int32)
+                same = (a == b) | (torch.isnan(d_new) & torch.isnan(d_ref))
+                exact_bad = int((~same[[1, 3, 4]]).sum())
+                moment_bits_differ = int((~same[[0, 2]]).sum())
+                with np.errstate(all='ignore'):
+                    rel = (d_new[[0, 2]] - d_ref[[0, 2]]).abs() / d_ref[[0, 2]].abs().clamp_min(1e-5)
+                got = d_new[:, idx].cpu().numpy()
+                obad = int((~((got[[1, 3, 4]] == oexact) | (np.isnan(got[[1, 3, 4]]) & np.isnan(oexact)))).sum())
+                ss[key] = {'kernel_ms': ms, 'frac': alg / (ms * 1e-3) / 1e9 / peak,
+                           'achieved': alg / (ms * 1e-3) / 1e9, 'unit': 'GB/s',
+                           'flagged_tiles': flagged,
+                           'order_stat_mismatches_vs_default': exact_bad,
+                           'order_stat_mismatches_vs_oracle': obad,
+                           'moment_values_not_bit_identical': moment_bits_differ,
+                           'max_rel_moment_vs_default': float(torch.nan_to_num(rel, nan=0.0).max())}
+                del d_new
+            except Exception as exc:                      # noqa: BLE001
+                ss[key] = {'error': repr(exc)[:300]}
+            finally:
+                stack.set_option('k2_algo', 0)
+                stack.set_option('k2_nw', 0)
+        out['k2_staged_select'] = ss
+    except Exception as exc:                              # noqa: BLE001
+        out['k2_staged_select'] = {'error': repr(exc)[:300]}
+
+    try:
+        nrec, rows = 16, 16
+        nbytes = nn * C4_WIDTH
+        dtext = torch.empty(rows * nbytes + 64, dtype=torch.uint8, device='cuda')
+        for r in range(rows):
+            _capi.check(L.gsb_encode_text_device(stack.handle, r, 0, nn, 12, 4, 1,
+                                                 dtext.data_ptr() + r * nbytes, None))
+        dec = _capi.Stack(1, rows * nn)
+        bad = torch.full((1,), -1, dtype=torch.int64, device='cuda')
+        reps = 10
+        for i in range(2):
+            e0.record()
+            for _ in range(reps if i else 2):
+                _capi.check(L.gsb_decode_text_device(dec.handle, 0, dtext.data_ptr(), rows * nbytes, 0,
+                                                     C4_WIDTH, 0, 0, rows * nn, bad.data_ptr(), None))
+            e1.record()
+            e1.synchronize()
+        k1_ms = e0.elapsed_time(e1) / reps
+        got = dec.download().reshape(rows, nn)
+        want = stack.download(0, rows)
+        k1_alg = (C4_WIDTH + 4.0) * rows * nn
+        out['k1_resident'] = {'records': rows * nn, 'text_bytes': rows * nbytes, 'kernel_ms': k1_ms,
+                              'achieved': k1_alg / (k1_ms * 1e-3) / 1e9, 'unit': 'GB/s',
+                              'frac': k1_alg / (k1_ms * 1e-3) / 1e9 / peak,
+                              'algorithmic_bytes': k1_alg,
+                              'l2': 'text + output = 288 MB per launch, larger than L2',
+                              'bad_line': int(bad.item()),
+                              'values_bit_identical': bool(np.array_equal(got.view(np.int32), want.view(np.int32)))}
+        dec.close()
+    except Exception as exc:                              # noqa: BLE001
+        out['k1_resident'] = {'error': repr(exc)[:300]}
+    grids.dump()
+    print(json.dumps({'extras': out}))
+
+
+def extras_subprocess(timeout=300):
+    """Runs ``bench.py --leg extras`` in its own process (own CUDA context, hard
+    time limit) and returns its JSON object; never raises."""
+    import subprocess
+    try:
+        r = subprocess.run([sys.executable, os.path.abspath(__file__), '--leg', 'extras'],
+                           capture_output=True, text=True, timeout=timeout,
+                           env=dict(os.environ, CUDA_VISIBLE_DEVICES=os.environ.get('CUDA_VISIBLE_DEVICES', '0').split(',')[0]))
+        for ln in reversed(r.stdout.strip().splitlines()):
+            if ln.startswith('{"extras"'):
+                return json.loads(ln)['extras']
+        return {'error': 'rc={0}: {1}'.format(r.returncode, (r.stderr or r.stdout)[-300:])}
+    except Exception as exc:                              # noqa: BLE001
+        return {'error': repr(exc)[:300]}
 
 
 # ------------------------------------------------------------------ config 4
@@ -792,8 +942,12 @@ def main():
     ap.add_argument('--impl', default='b200')
     ap.add_argument('--config', type=int, default=3, choices=[3, 4, 5])
     ap.add_argument('--scaling', default='strong', choices=['strong', 'weak'])
+    ap.add_argument('--leg', default=None, choices=['extras'],
+                    help='internal: the subprocess leg of the default run')
     args = ap.parse_args()
-    if args.impl == 'reference':
+    if args.leg == 'extras':
+        run_extras(args)
+    elif args.impl == 'reference':
         run_reference(args)
     elif args.config == 4:
         run_cfg4(args)
