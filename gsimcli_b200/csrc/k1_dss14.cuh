@@ -30,6 +30,13 @@ K1_HD unsigned k1_notdigit(unsigned u) {      // 0x80 per non-digit byte
 K1_HD unsigned k1_nonzero(unsigned z) {       // 0x80 per non-zero byte
     return (((z & 0x7f7f7f7fu) + 0x7f7f7f7fu) | z) & 0x80808080u;
 }
+#ifdef __CUDA_ARCH__
+// the exact division is needed for about one record in 10^7; kept out of line so
+// that the compiler cannot if-convert it into the common path (inlined, its
+// reciprocal iteration -- MUFU.RCP64H + 7 DFMA/DMUL + fix-up tests -- ran for
+// every record and the result was thrown away by a select)
+__device__ __noinline__ double k1_div1e4_exact(double m) { return __ddiv_rn(m, 1.0e4); }
+#endif
 K1_HD unsigned k1_digits4(unsigned t) {       // 4 digit bytes (byte 0 first) -> number
     t = (t * 10u + (t >> 8)) & 0x00ff00ffu;
     return (t * 100u + (t >> 16)) & 0xffffu;
@@ -79,7 +86,7 @@ K1_HD bool k1_parse_dss14_words(unsigned u0, unsigned u1, unsigned u2, unsigned 
     const unsigned low = static_cast<unsigned>(xb) & 0x1fffffffu;
     if (((low + 16u) & 0x0fffffffu) < 32u) {
 #ifdef __CUDA_ARCH__
-        x = __ddiv_rn(m, 1.0e4);
+        x = k1_div1e4_exact(m);
 #else
         x = m / 1.0e4;
 #endif
