@@ -582,7 +582,8 @@ def run_extras(args):
       option k2_algo = 4) on the reference's call shape, 16 and 32 warps, 10^6
       columns of the benchmark stack, checked against the default kernel's maps
       (bit for bit) and the oracle;
-    * K1 on resident text larger than L2 (16 x 10^6 DSS records = 224 MB).
+    * K1 on resident text larger than L2 (16 x 10^6 DSS records = 224 MB): the
+      default kernel and the experimental 8-records-per-thread one (k1_algo = 1).
     Prints one JSON object; every part carries its own ``error`` on failure."""
     import torch
     from gsimcli_b200 import _capi, synth
@@ -663,28 +664,33 @@ def run_extras(args):
         for r in range(rows):
             _capi.check(L.gsb_encode_text_device(stack.handle, r, 0, nn, 12, 4, 1,
                                                  dtext.data_ptr() + r * nbytes, None))
-        dec = _capi.Stack(1, rows * nn)
-        bad = torch.full((1,), -1, dtype=torch.int64, device='cuda')
-        reps = 10
-        for i in range(2):
-            e0.record()
-            for _ in range(reps if i else 2):
-                _capi.check(L.gsb_decode_text_device(dec.handle, 0, dtext.data_ptr(), rows * nbytes, 0,
-                                                     C4_WIDTH, 0, 0, rows * nn, bad.data_ptr(), None))
-            e1.record()
-            e1.synchronize()
-        k1_ms = e0.elapsed_time(e1) / reps
-        got = dec.download().reshape(rows, nn)
         want = stack.download(0, rows)
         k1_alg = (C4_WIDTH + 4.0) * rows * nn
-        out['k1_resident'] = {'records': rows * nn, 'text_bytes': rows * nbytes, 'kernel_ms': k1_ms,
-                              'achieved': k1_alg / (k1_ms * 1e-3) / 1e9, 'unit': 'GB/s',
-                              'frac': k1_alg / (k1_ms * 1e-3) / 1e9 / peak,
-                              'algorithmic_bytes': k1_alg,
-                              'l2': 'text + output = 288 MB per launch, larger than L2',
-                              'bad_line': int(bad.item()),
-                              'values_bit_identical': bool(np.array_equal(got.view(np.int32), want.view(np.int32)))}
-        dec.close()
+        k1 = {'records': rows * nn, 'text_bytes': rows * nbytes, 'algorithmic_bytes': k1_alg,
+              'l2': 'text + output = 288 MB per launch, larger than L2'}
+        # the default kernel, then the experimental 8-records-per-thread one (k1_algo = 1)
+        for name, algo in (('default', 0), ('dss14x8', 1)):
+            try:
+                dec = _capi.Stack(1, rows * nn)
+                dec.set_option('k1_algo', algo)
+                bad = torch.full((1,), -1, dtype=torch.int64, device='cuda')
+                reps = 10
+                for i in range(2):
+                    e0.record()
+                    for _ in range(reps if i else 2):
+                        _capi.check(L.gsb_decode_text_device(dec.handle, 0, dtext.data_ptr(), rows * nbytes, 0,
+                                                             C4_WIDTH, 0, 0, rows * nn, bad.data_ptr(), None))
+                    e1.record()
+                    e1.synchronize()
+                k1_ms = e0.elapsed_time(e1) / reps
+                got = dec.download().reshape(rows, nn)
+                k1[name] = {'kernel_ms': k1_ms, 'achieved': k1_alg / (k1_ms * 1e-3) / 1e9, 'unit': 'GB/s',
+                            'frac': k1_alg / (k1_ms * 1e-3) / 1e9 / peak, 'bad_line': int(bad.item()),
+                            'values_bit_identical': bool(np.array_equal(got.view(np.int32), want.view(np.int32)))}
+                dec.close()
+            except Exception as exc:                      # noqa: BLE001
+                k1[name] = {'error': repr(exc)[:300]}
+        out['k1_resident'] = k1
     except Exception as exc:                              # noqa: BLE001
         out['k1_resident'] = {'error': repr(exc)[:300]}
     grids.dump()

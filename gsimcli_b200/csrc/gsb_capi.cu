@@ -222,6 +222,11 @@ int gsb_stack_set_option(gsb_stack* s, const char* key, int64_t value) {
         s->k2_algo = (int)value;
         return GSB_OK;
     }
+    if (strcmp(key, "k1_algo") == 0) {
+        GSB_REQUIRE(value == 0 || value == 1, "k1_algo must be 0 or 1");
+        s->k1_algo = (int)value;
+        return GSB_OK;
+    }
     if (strcmp(key, "k2_nw") == 0) {
         GSB_REQUIRE(value == 0 || value == 16 || value == 32, "k2_nw must be 0, 16 or 32");
         s->k2_nw = (int)value;

@@ -57,6 +57,7 @@ struct gsb_stack {
     int k2_algo;           // tests only: 0 = default, 1 = counting sort, 2 = bitonic, 3 = register tile, 4 = staged select
     int k2_nw;             // tests only: warps per CTA of the register-tile kernel (0 = default)
     int k2_stats;          // diagnostic counters of the counting-sort kernel
+    int k1_algo;           // tests only: 1 = the experimental 8-records-per-thread DSS decoder
     int* k2_flags;         // device, [0] count + one slot per 32-node tile: tiles the register-
                            // tile kernel hands to the counting-sort kernel (own buffer: K2 may
                            // run concurrently with calls that regrow `scratch` on other streams)

@@ -300,6 +300,72 @@ k1_decode_fixed(const char* __restrict__ text, long long nbytes, int W, long lon
     }
 }
 
+// ------------------------------------------------------------ DSS records, 8 per thread
+// EXPERIMENTAL (stack option "k1_algo" = 1, never the default: written after the
+// round's GPU budget was spent; bench.py times it in its `experimental` leg and
+// compares the decoded values bit for bit with the default kernel's).
+// '%12.4f\r\n' records are 14 bytes, so 8 of them are 112 bytes = seven 16-byte
+// vectors: a thread loads them straight into registers (no shared-memory staging,
+// no per-line word loads), every record starts at a compile-time word / half-word
+// position (even records are word aligned, odd ones 16 bits in), and the 8 results
+// leave as two 16-byte stores.  Same parser (k1_dss14.cuh), same fall-back parsers
+// for any record it refuses.  Needs the first record 16-byte aligned.
+// any spelling the record parser refuses: the general parsers, from global memory
+// (out of line: it is inlined nowhere near the common path)
+__device__ __noinline__ void k1_dss14_slow(const char* text, long long nbytes, long long li, float* out,
+                                           long long* bad_line) {
+    const long long off = li * 14;
+    const unsigned char* lp = reinterpret_cast<const unsigned char*>(text) + off;
+    float val;
+    const bool ok = (lp[13] == '\n') &&
+                    ((off + 24 <= nbytes && parse_fixed_fast(lp, 14, &val)) || parse_float(lp, 14, &val));
+    if (ok) out[li] = val;
+    else atomicMin(reinterpret_cast<unsigned long long*>(bad_line), static_cast<unsigned long long>(li));
+}
+
+template <bool VEC_STORE>
+__global__ void __launch_bounds__(K1_THREADS)
+k1_decode_dss14x8(const char* __restrict__ text, long long nbytes, long long nlines,
+                  float* __restrict__ out, long long* bad_line) {
+    const long long g = static_cast<long long>(blockIdx.x) * K1_THREADS + threadIdx.x;
+    const long long ngroups = nlines >> 3;
+    if (g > ngroups) return;
+    auto slow = [&](long long li) { k1_dss14_slow(text, nbytes, li, out, bad_line); };
+    if (g == ngroups) {                 // the last nlines % 8 records
+        for (long long li = ngroups * 8; li < nlines; ++li) slow(li);
+        return;
+    }
+    const uint4* p = reinterpret_cast<const uint4*>(text + g * 112);
+    unsigned w[28];
+#pragma unroll
+    for (int k = 0; k < 7; ++k) {
+        const uint4 v = __ldg(p + k);
+        w[4 * k] = v.x; w[4 * k + 1] = v.y; w[4 * k + 2] = v.z; w[4 * k + 3] = v.w;
+    }
+    float f[8];
+    unsigned okmask = 0;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        if (k1_parse_dss14_group(w, k, &f[k])) okmask |= 1u << k;   // k is compile-time after unrolling
+    }
+    float* o = out + g * 8;
+    if (okmask == 0xffu) {
+        if (VEC_STORE) {
+            reinterpret_cast<float4*>(o)[0] = make_float4(f[0], f[1], f[2], f[3]);
+            reinterpret_cast<float4*>(o)[1] = make_float4(f[4], f[5], f[6], f[7]);
+        } else {
+#pragma unroll
+            for (int k = 0; k < 8; ++k) o[k] = f[k];
+        }
+    } else {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            if (okmask & (1u << k)) o[k] = f[k];
+            else slow(g * 8 + k);
+        }
+    }
+}
+
 // ------------------------------------------------------------ general form
 // pass 1: newline count per block (each thread 16 bytes)
 __global__ void __launch_bounds__(K1_THREADS)
@@ -486,6 +552,19 @@ int gsb_launch_decode(gsb_stack* s, int64_t r, const char* dtext, size_t nbytes,
         nbytes -= static_cast<size_t>(first_line) * line_width;
         GSB_REQUIRE(line_width >= 2 && line_width <= 64, "line_width %d out of range",
                     line_width);
+        if (s->k1_algo == 1 && line_width == 14 && (reinterpret_cast<uintptr_t>(dtext) & 15) == 0) {
+            // experimental: 8 records per thread (k1_decode_dss14x8)
+            const long long threads = (nlines >> 3) + 1;
+            const int blocks8 = static_cast<int>((threads + K1_THREADS - 1) / K1_THREADS);
+            if ((reinterpret_cast<uintptr_t>(out) & 15) == 0)
+                k1_decode_dss14x8<true><<<blocks8, K1_THREADS, 0, st>>>(
+                    dtext, static_cast<long long>(nbytes), nlines, out, reinterpret_cast<long long*>(d_bad_line));
+            else
+                k1_decode_dss14x8<false><<<blocks8, K1_THREADS, 0, st>>>(
+                    dtext, static_cast<long long>(nbytes), nlines, out, reinterpret_cast<long long*>(d_bad_line));
+            GSB_CUDA(cudaGetLastError());
+            return GSB_OK;
+        }
         const long long blocks = (nlines + K1_LPB - 1) / K1_LPB;
         const size_t smem = static_cast<size_t>(K1_LPB) * line_width + 48;
         GSB_CUDA(cudaFuncSetAttribute(k1_decode_fixed,

@@ -95,3 +95,19 @@ K1_HD bool k1_parse_dss14_words(unsigned u0, unsigned u1, unsigned u2, unsigned 
     *out = static_cast<float>(x);
     return true;
 }
+
+// Record k (0..7) of a group of 8 records = 112 bytes held as 28 little-endian
+// words (k1_decode_dss14x8): even records start on a word, odd ones 16 bits in.
+K1_HD bool k1_parse_dss14_group(const unsigned (&w)[28], int k, float* out) {
+    const int b = (14 * k) >> 2;
+    unsigned u0, u1, u2, u3;
+    if ((k & 1) == 0) {
+        u0 = w[b]; u1 = w[b + 1]; u2 = w[b + 2]; u3 = w[b + 3];
+    } else {
+        u0 = (w[b] >> 16) | (w[b + 1] << 16);
+        u1 = (w[b + 1] >> 16) | (w[b + 2] << 16);
+        u2 = (w[b + 2] >> 16) | (w[b + 3] << 16);
+        u3 = w[b + 3] >> 16;
+    }
+    return k1_parse_dss14_words(u0, u1, u2, u3, out);
+}

@@ -24,3 +24,19 @@ extern "C" void k1_dss14_emulate(const unsigned char* text, long long nlines, fl
         out[i] = v;
     }
 }
+
+// the 8-records-per-thread form (k1_decode_dss14x8): groups of 112 bytes as 28
+// words, record k taken from its compile-time word / half-word position.
+// nlines must be a multiple of 8.
+extern "C" void k1_dss14_emulate_x8(const unsigned char* text, long long nlines, float* out,
+                                    unsigned char* ok) {
+    for (long long g = 0; g < nlines / 8; ++g) {
+        unsigned w[28];
+        memcpy(w, text + g * 112, 112);
+        for (int k = 0; k < 8; ++k) {
+            float v = 0.f;
+            ok[g * 8 + k] = k1_parse_dss14_group(w, k, &v) ? 1 : 0;
+            out[g * 8 + k] = v;
+        }
+    }
+}

@@ -84,3 +84,35 @@ def test_wrong_line_ending_is_rejected(k1):
         ok = np.zeros(1, np.uint8)
         lib.k1_dss14_emulate(text.ctypes.data, 1, out.ctypes.data, ok.ctypes.data)
         assert ok[0] == 0
+
+
+def test_eight_records_per_thread_form_agrees_with_the_per_record_form():
+    """k1_decode_dss14x8 (experimental, stack option k1_algo = 1) takes record k of
+    a 112-byte group from a compile-time word / half-word position: same values,
+    same accept / reject decisions as the per-record form, at every position of
+    the group, for good and malformed records."""
+    lib = C.CDLL(build_emul.build_k1())
+    for f in (lib.k1_dss14_emulate, lib.k1_dss14_emulate_x8):
+        f.restype = None
+        f.argtypes = [C.c_void_p, C.c_longlong, C.c_void_p, C.c_void_p]
+    rng = np.random.default_rng(9)
+    vals = np.round(rng.uniform(-999999.0, 9999999.0, size=80000), 4)
+    lines = ['%12.4f' % v for v in vals]
+    bad = [b.rjust(12)[:12] for b in BAD]
+    for i, pos in enumerate(rng.integers(0, len(lines), size=4000)):
+        lines[pos] = bad[i % len(bad)]
+    text = np.frombuffer(''.join(s + '\r\n' for s in lines).encode('latin-1'), dtype=np.uint8).copy()
+    # wrong line endings at every position of a group
+    for k in range(8):
+        text[14 * (800 + 9 * k) + 12: 14 * (800 + 9 * k) + 14] = (10, 13)
+    n = len(lines)
+    o1, k1_ = np.zeros(n, np.float32), np.zeros(n, np.uint8)
+    o2, k2_ = np.zeros(n, np.float32), np.zeros(n, np.uint8)
+    lib.k1_dss14_emulate(text.ctypes.data, n, o1.ctypes.data, k1_.ctypes.data)
+    lib.k1_dss14_emulate_x8(text.ctypes.data, n, o2.ctypes.data, k2_.ctypes.data)
+    assert np.array_equal(k1_, k2_)
+    assert 3000 < int((k1_ == 0).sum()) < 4100
+    good = k1_ == 1
+    assert np.array_equal(o1[good].view(np.int32), o2[good].view(np.int32))
+    exp = np.array([np.float32(float(s)) for s, g in zip(lines, good) if g], dtype=np.float32)
+    assert np.array_equal(o2[good].view(np.int32), exp.view(np.int32))
