@@ -102,7 +102,8 @@ int gsb_stack_info(const gsb_stack* s, int64_t* R, int64_t* N, int64_t* pitch,
  * 1 = counting sort, 2 = register bitonic for every R, 3 = register tile, 4 = the
  * experimental staged-select kernel for the reference's call shape -- other shapes
  * take the register tile), "k2_nw" the warps per CTA of the register-tile /
- * staged-select kernel, "k2_stats" enables gsb_debug_cs_counters. */
+ * staged-select kernel, "k2_stats" enables gsb_debug_cs_counters, "k1_algo" = 1
+ * sends '%12.4f CRLF' text to the experimental 8-records-per-thread decoder. */
 int gsb_stack_set_option(gsb_stack* s, const char* key, int64_t value);
 /* diagnostic: number of 32-node tiles of the last gsb_stats_grid call on this
  * stack that the register-tile kernel handed to the counting-sort kernel
