@@ -965,3 +965,56 @@ def test_stock_call_shape_default_dispatch_subranges(R):
     torch.cuda.synchronize()
     assert np.array_equal(maps.numpy().view(np.int32), res.view(np.int32))
     stack.close()
+
+
+# ---------------------------------------------------------------------------
+# Experimental kernels (written after the round's GPU budget was spent; never
+# the default dispatch).  They have not run on a device at commit time, so these
+# tests are opt-in: GSB_TEST_EXPERIMENTAL=1 python -m pytest tests -m gpu -k experimental
+# (bench.py measures and checks the same kernels in its subprocess leg).
+EXPERIMENTAL = pytest.mark.skipif(not os.environ.get('GSB_TEST_EXPERIMENTAL'),
+                                  reason='experimental kernels: set GSB_TEST_EXPERIMENTAL=1')
+ALGOS['ssel16'] = (4, 16)
+ALGOS['ssel32'] = (4, 32)
+
+
+@EXPERIMENTAL
+@pytest.mark.parametrize('algo', ['ssel16', 'ssel32'])
+@pytest.mark.parametrize('R', [129, 200, 333, 500, 1000, 1024])
+def test_experimental_staged_select_kernel(algo, R):
+    rng = np.random.default_rng(R)
+    st = synth.stack(3000 + R, R, [16, 11, 4])
+    st[:, 3] = 812.5
+    st[:, 4] = np.float32(ND)
+    st[:, 5] = np.float32(ND)
+    st[R // 2, 5] = 640.25
+    st[:, 6] = np.float32(ND)
+    st[0, 6], st[R - 1, 6] = 7.5, 8.5
+    st[:, 8] = np.where(np.arange(R) % 2 == 0, 500.0, 600.0)
+    st[:, 9] = rng.integers(0, 5, size=R) * 0.5                        # heavy ties -> flagged tile
+    st[0, 11] = 3.0e8                                                  # outlier -> flagged tile
+    for p in (0.95, 0.5, 1.0, 0.1):
+        check_grid(st, p=p, percentiles=None, mode=False, algo=algo)
+    check_grid(st, p=0.9, percentiles=None, mode=False, n0=37, nn=100, algo=algo)   # sub-range
+    check_grid(st, p=0.9, percentiles=[0.0], mode=False, algo=algo)    # 4 quantile planes: register tile
+
+
+@EXPERIMENTAL
+def test_experimental_k1_eight_records_per_thread():
+    rng = np.random.default_rng(5)
+    n = 100003                                         # not a multiple of 8: the tail thread
+    vals = np.round(rng.uniform(-99999.0, 999999.0, size=n), 4).astype(np.float32)
+    lines = ['%12.4f' % v for v in vals]
+    lines[77] = '   1.25e+002'                         # refused by the record parser: general parser
+    lines[n - 2] = '     +12.5000'[-12:]
+    text = ''.join(s + '\r\n' for s in lines).encode('ascii')
+    exp = np.array([np.float32(float(s)) for s in lines], dtype=np.float32)
+    got = []
+    for algo in (0, 1):
+        stack = _capi.Stack(1, n)
+        stack.set_option('k1_algo', algo)
+        stack.decode_text(0, text, 0, 14)
+        got.append(stack.download()[0])
+        stack.close()
+    assert np.array_equal(got[0].view(np.int32), exp.view(np.int32))
+    assert np.array_equal(got[1].view(np.int32), exp.view(np.int32))
