@@ -185,3 +185,77 @@ def test_save_output_gsimcli_format_matches_reference(tmp_path):
     sa = pd.read_csv(str(tmp_path / 'ref_stations.csv'), index_col=0)
     sb = pd.read_csv(str(tmp_path / 'mine_stations.csv'), index_col=0)
     assert sa.equals(sb)
+
+
+@pytest.mark.parametrize('seed', [11, 12, 13, 14, 15, 16])
+def test_detect_every_method_on_fresh_stacks(tmp_path, seed):
+    """All four correction methods, discs of radius 0..2, several detection
+    probabilities, R even and odd, on stacks and observed series drawn from the
+    seed: the reference's detect() (tools/homog.py:27-276, through GridFiles.
+    stats_area) and the oracle agree on the counts, the flags and every value
+    of the homogenised frame."""
+    _, grid, homog = refshim.load_reference()
+    rng = np.random.default_rng(seed)
+    dims, first, cells = [9, 8, 5 + seed % 3], [500.0, 100.0, 1970], [25.0, 50.0, 1]
+    R = 8 + seed % 5
+    st = synth.stack(seed, R, dims).astype(np.float64)
+    st[st == np.float64(np.float32(ND))] = ND
+    g = _load(tmp_path, st, dims, first, cells)
+    cols = ['x', 'y', 'time', 'station', 'clim']
+    cases = [dict(method='mean'), dict(method='median'),
+             dict(method='skewness', skewness=0.3), dict(method='skewness', skewness=5.0),
+             dict(method='percentile', percentile=0.9), dict(method='percentile', percentile=0.25)]
+    checked = 0
+    for s in synth.stations(seed, 3, R, dims, first, cells, tol=2):
+        obs = pd.DataFrame(np.array(s['obs'], dtype=np.float64), columns=cols)
+        for kw in cases:
+            for rad in (0, 1, 2):
+                prob = float(rng.choice([0.8, 0.9, 0.95, 0.99]))
+                g.reset_read()
+                cand = grid.PointSet('cand', ND, 5, list(cols), obs.copy())
+                with warnings.catch_warnings():
+                    warnings.simplefilter('ignore')
+                    hom, dn, md = homog.detect(g, cand, rad=rad, prob=prob, **kw)
+                ohom, odn, omd = O.detect(st, dims, first, cells, ND, obs.copy(), ND,
+                                          rad=rad, prob=prob, **kw)
+                assert (dn, md) == (odn, omd), (kw, rad, prob)
+                assert list(hom.values.columns) == list(ohom.columns)
+                np.testing.assert_allclose(hom.values.values.astype(float),
+                                           ohom.values.astype(float), rtol=5e-13, atol=1e-10,
+                                           equal_nan=True)
+                checked += 1
+    assert checked == 54
+
+
+@pytest.mark.parametrize('seed', [21, 22, 23, 24])
+def test_stats_every_map_on_fresh_stacks_with_edge_columns(tmp_path, seed):
+    """GridFiles.stats of the reference (tools/grid.py:601-735: bottleneck nan*
+    functions, pandas skew / quantile) against the oracle on a fresh stack with
+    the columns whose numerics are corner cases: constant, empty, n = 1, n = 2,
+    two atoms, heavy ties, a zero-inflated one; even and odd R, three p."""
+    rng = np.random.default_rng(seed)
+    dims, first, cells = [7, 6, 3], [0.0, 0.0, 1], [1.0, 1.0, 1]
+    R = 9 + seed % 4
+    st = synth.stack(seed, R, dims).astype(np.float64)
+    st[st == np.float64(np.float32(ND))] = ND
+    st[:, 3] = 812.5
+    st[:, 4] = ND
+    st[:, 5] = ND
+    st[R // 2, 5] = 640.25
+    st[:, 6] = ND
+    st[0, 6], st[R - 1, 6] = 7.5, 8.5
+    st[:, 8] = np.where(np.arange(R) % 2 == 0, 500.0, 600.0)
+    st[:, 9] = rng.integers(0, 3, size=R) * 0.5
+    st[:, 10] = np.where(rng.uniform(size=R) < 0.7, 0.0, np.round(rng.gamma(2.0, 20.0, size=R), 4))
+    g = _load(tmp_path, st, dims, first, cells)
+    for p in (0.95, 0.8, 0.5):
+        g.reset_read()
+        with warnings.catch_warnings():
+            warnings.simplefilter('ignore')
+            ref = g.stats(p=p, **ALL)
+            mine = O.grid_stats(st, ND, ALLF, p)
+        for key in ref:
+            np.testing.assert_allclose(mine[key], ref[key].val, rtol=5e-13, atol=1e-10,
+                                       equal_nan=True, err_msg=key)
+        assert np.array_equal(mine['medianmap'], ref['medianmap'].val, equal_nan=True)
+        assert np.array_equal(mine['percmap'], ref['percmap'].val, equal_nan=True)
