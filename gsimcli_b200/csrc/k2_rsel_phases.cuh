@@ -100,25 +100,29 @@ RS_HD float pinf() { return u2f(0x7f800000u); }
 // bn.replace(arr, nodata, nan) + NaN dropping (grid.py:681): false for NaN
 RS_HD bool valid(float x, float nodata) { return (x == x) && (x != nodata); }
 
+// (host forms: real atomics, so that the emulations may also run the phases with
+// one OS thread per CUDA thread -- tests/emul/k2_ssel_threads.cpp)
 RS_HD uint32_t atomic_add(uint32_t* p, uint32_t v) {
 #ifdef __CUDA_ARCH__
     return atomicAdd(p, v);
 #else
-    const uint32_t o = *p; *p = o + v; return o;
+    return __atomic_fetch_add(p, v, __ATOMIC_RELAXED);
 #endif
 }
 RS_HD void atomic_max_u32(uint32_t* p, uint32_t v) {
 #ifdef __CUDA_ARCH__
     atomicMax(p, v);
 #else
-    if (v > *p) *p = v;
+    uint32_t o = __atomic_load_n(p, __ATOMIC_RELAXED);
+    while (v > o && !__atomic_compare_exchange_n(p, &o, v, false, __ATOMIC_RELAXED, __ATOMIC_RELAXED)) {}
 #endif
 }
 RS_HD void atomic_max_u64(unsigned long long* p, unsigned long long v) {
 #ifdef __CUDA_ARCH__
     atomicMax(p, v);
 #else
-    if (v > *p) *p = v;
+    unsigned long long o = __atomic_load_n(p, __ATOMIC_RELAXED);
+    while (v > o && !__atomic_compare_exchange_n(p, &o, v, false, __ATOMIC_RELAXED, __ATOMIC_RELAXED)) {}
 #endif
 }
 RS_HD double dmul(double a, double b) {
@@ -352,7 +356,7 @@ RS_HD void phase_b(const Thr<IPT>& t, const Smem& s, int c) {
 #ifdef __CUDA_ARCH__
         asm volatile("red.shared.add.u32 [%0], 1;" ::"r"(static_cast<uint32_t>(__cvta_generic_to_shared(cells + b * COLS))) : "memory");
 #else
-        cells[b * COLS] += 1u;
+        __atomic_fetch_add(cells + b * COLS, 1u, __ATOMIC_RELAXED);
 #endif
     }
 }

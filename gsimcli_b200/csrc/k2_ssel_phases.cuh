@@ -98,16 +98,27 @@ RS_HD void atomic_min_u32(uint32_t* p, uint32_t v) {
 #ifdef __CUDA_ARCH__
     atomicMin(p, v);
 #else
-    if (v < *p) *p = v;
+    uint32_t o = __atomic_load_n(p, __ATOMIC_RELAXED);
+    while (v < o && !__atomic_compare_exchange_n(p, &o, v, false, __ATOMIC_RELAXED, __ATOMIC_RELAXED)) {}
 #endif
 }
 RS_HD uint32_t atomic_cas_u32(uint32_t* p, uint32_t expect, uint32_t v) {
 #ifdef __CUDA_ARCH__
     return atomicCAS(p, expect, v);
 #else
-    const uint32_t o = *p;
-    if (o == expect) *p = v;
-    return o;
+    uint32_t o = expect;
+    __atomic_compare_exchange_n(p, &o, v, false, __ATOMIC_RELAXED, __ATOMIC_RELAXED);
+    return o;                      // the old value: `expect` on success
+#endif
+}
+
+// a word other warps may be claiming by compare-and-swap at the same time (phase L:
+// only the mark in the high half changes, the reader masks it off)
+RS_HD uint32_t ld_racy(const uint32_t* p) {
+#ifdef __CUDA_ARCH__
+    return *reinterpret_cast<const volatile uint32_t*>(p);
+#else
+    return __atomic_load_n(p, __ATOMIC_RELAXED);
 #endif
 }
 
@@ -271,7 +282,7 @@ RS_HD void phase_b(const Thr<IPT>& t, const Smem& s, int c) {
 #ifdef __CUDA_ARCH__
         asm volatile("red.shared.add.u32 [%0], 1;" ::"r"(static_cast<uint32_t>(__cvta_generic_to_shared(cells + b * COLS))) : "memory");
 #else
-        cells[b * COLS] += 1u;
+        __atomic_fetch_add(cells + b * COLS, 1u, __ATOMIC_RELAXED);
 #endif
     }
 }
@@ -336,12 +347,12 @@ RS_HD void phase_locate(const Thr<IPT>& t, const Smem& s, const Args& a, int w, 
 #pragma unroll 8
             for (int i = 0; i < CH; ++i) {
                 const int b = b0 + i;
-                const uint32_t cnt = b < NBINS ? (s.cells[b * COLS + c] & COUNT_MASK) : 0u;
+                const uint32_t cnt = b < NBINS ? (ld_racy(s.cells + b * COLS + c) & COUNT_MASK) : 0u;
                 cumb += cnt;
                 if (cumb <= r && b + 1 < NBINS) { bsel = b + 1; start = cumb; }
             }
             uint32_t* cell = s.cells + bsel * COLS + c;
-            const uint32_t cnt = *cell & COUNT_MASK;
+            const uint32_t cnt = ld_racy(cell) & COUNT_MASK;
             const uint32_t old = atomic_cas_u32(cell, cnt, cnt | (static_cast<uint32_t>(j + 1) << MARK_SHIFT));
             const uint32_t lid = (old >> MARK_SHIFT) ? (old >> MARK_SHIFT) - 1u : static_cast<uint32_t>(j);
             const uint32_t kind = bsel == 0 ? 1u : bsel == NBINS - 1 ? 2u : 0u;

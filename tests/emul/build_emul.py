@@ -53,3 +53,22 @@ def build_ssel(force=False, sanitize=False):
     subprocess.run(['g++'] + flags + ['-std=c++17', '-ffp-contract=off', '-Wno-unknown-pragmas',
                     '-shared', '-fPIC', '-o', lib, SSEL_SRC], check=True)
     return lib
+
+
+SSEL_MAIN = os.path.join(HERE, 'k2_ssel_tsan_main.cpp')
+SSEL_THR = os.path.join(HERE, 'k2_ssel_threads.cpp')
+SSEL_KRN = os.path.join(HERE, '..', '..', 'gsimcli_b200', 'csrc', 'k2_ssel_kernel.cuh')
+
+
+def build_ssel_threads(sanitizer=None, force=False):
+    """Stand-alone driver of the THREADED emulation of the staged-select kernel
+    (k2_ssel_kernel.cuh run with one OS thread per CUDA thread):
+    ``sanitizer`` = None, 'thread' or 'address'.  Returns the executable."""
+    exe = os.path.join(HERE, 'k2_ssel_threads_' + (sanitizer or 'plain'))
+    srcs = [SSEL_MAIN, SSEL_THR, SSEL_SRC, SSEL_HDR, SSEL_KRN, HDR]
+    if not force and os.path.exists(exe) and os.path.getmtime(exe) >= max(os.path.getmtime(f) for f in srcs):
+        return exe
+    flags = ['-fsanitize=' + sanitizer + (',undefined' if sanitizer == 'address' else '')] if sanitizer else []
+    subprocess.run(['g++', '-O1', '-g', '-std=c++17', '-pthread', '-ffp-contract=off',
+                    '-Wno-unknown-pragmas'] + flags + ['-o', exe, SSEL_MAIN], check=True)
+    return exe
