@@ -72,3 +72,24 @@ def build_ssel_threads(sanitizer=None, force=False):
     subprocess.run(['g++', '-O1', '-g', '-std=c++17', '-pthread', '-ffp-contract=off',
                     '-Wno-unknown-pragmas'] + flags + ['-o', exe, SSEL_MAIN], check=True)
     return exe
+
+
+CSORT_SRC = os.path.join(HERE, 'k2_csort_threads.cpp')
+CSORT_DEPS = [CSORT_SRC, os.path.join(HERE, 'cuda_threads_shim.h'), SRC, HDR,
+              os.path.join(HERE, '..', '..', 'gsimcli_b200', 'csrc', 'k2_csort_kernel.cuh'),
+              os.path.join(HERE, '..', '..', 'gsimcli_b200', 'csrc', 'k2_args.cuh'),
+              os.path.join(HERE, '..', '..', 'gsimcli_b200', 'csrc', 'gsb_common.cuh')]
+
+
+def build_csort_threads(sanitizer=None, force=False):
+    """Stand-alone driver of the THREADED emulation of the counting-sort kernel
+    (csrc/k2_csort_kernel.cuh on the CUDA model of cuda_threads_shim.h):
+    ``sanitizer`` = None or 'thread'.  Needs the CUDA headers (types only)."""
+    exe = os.path.join(HERE, 'k2_csort_threads_' + (sanitizer or 'plain'))
+    if not force and os.path.exists(exe) and os.path.getmtime(exe) >= max(os.path.getmtime(f) for f in CSORT_DEPS):
+        return exe
+    cuda_inc = os.path.join(os.environ.get('CUDA_HOME', '/usr/local/cuda'), 'include')
+    flags = ['-fsanitize=' + sanitizer, '-Wno-tsan'] if sanitizer else []
+    subprocess.run(['g++', '-O1', '-g', '-std=c++17', '-pthread', '-ffp-contract=off', '-Wno-unknown-pragmas',
+                    '-Wno-attributes', '-I' + cuda_inc] + flags + ['-o', exe, CSORT_SRC], check=True)
+    return exe

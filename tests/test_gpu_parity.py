@@ -967,6 +967,22 @@ def test_stock_call_shape_default_dispatch_subranges(R):
     stack.close()
 
 
+def test_moments_with_leading_realizations_missing():
+    """Columns whose first 32 (and more) realizations are missing, narrow and far
+    from zero (mean / sigma = 40): the pivot of the float32 shifted sums must come
+    from the first realizations that exist.  (The counting-sort kernel took 0 and
+    lost 38 % of the skewness of such a column; found by running the kernel on the
+    CPU, tests/test_k2_csort_emul.py.)"""
+    rng = np.random.default_rng(41)
+    for R in (100, 200, 1000):
+        st = np.round(rng.normal(800.0, 20.0, size=(R, 64)) * 16) / 16
+        st[:40, 8:24] = ND
+        st[:R // 3, 24:32] = ND
+        st[:R - 5, 32:36] = ND                      # five values left
+        check_grid(st)                                # full call: counting sort
+        check_grid(st, percentiles=None, mode=False)  # the reference's call: register tile at R >= 200
+
+
 # ---------------------------------------------------------------------------
 # Experimental kernels (written after the round's GPU budget was spent; never
 # the default dispatch).  They have not run on a device at commit time, so these
