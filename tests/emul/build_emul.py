@@ -93,3 +93,15 @@ def build_csort_threads(sanitizer=None, force=False):
     subprocess.run(['g++', '-O1', '-g', '-std=c++17', '-pthread', '-ffp-contract=off', '-Wno-unknown-pragmas',
                     '-Wno-attributes', '-I' + cuda_inc] + flags + ['-o', exe, CSORT_SRC], check=True)
     return exe
+
+
+def build_csort_lib(force=False):
+    """The same emulation as a shared library (k2_csort_emulate_threads)."""
+    lib = os.path.join(HERE, 'libk2csort_threads.so')
+    if not force and os.path.exists(lib) and os.path.getmtime(lib) >= max(os.path.getmtime(f) for f in CSORT_DEPS):
+        return lib
+    cuda_inc = os.path.join(os.environ.get('CUDA_HOME', '/usr/local/cuda'), 'include')
+    subprocess.run(['g++', '-O2', '-std=c++17', '-pthread', '-ffp-contract=off', '-Wno-unknown-pragmas',
+                    '-Wno-attributes', '-DCSORT_LIB', '-I' + cuda_inc, '-shared', '-fPIC', '-o', lib, CSORT_SRC],
+                   check=True)
+    return lib

@@ -118,8 +118,10 @@ static inline void __threadfence_block() { std::atomic_thread_fence(std::memory_
 static inline long long clock64() { return 0; }
 static inline int __popc(unsigned v) { return __builtin_popcount(v); }
 static inline int __ffs(unsigned v) { return __builtin_ffs(static_cast<int>(v)); }
-static inline unsigned __float_as_uint(float f) { unsigned u; memcpy(&u, &f, 4); return u; }
-static inline int __float_as_int(float f) { int u; memcpy(&u, &f, 4); return u; }
+// a NaN PRODUCED by GPU arithmetic is the canonical 0x7fffffff; x86 produces the
+// negative default NaN (INF * 0 in the bin map of an empty column): same bits here
+static inline unsigned __float_as_uint(float f) { unsigned u; memcpy(&u, &f, 4); return f != f ? 0x7fffffffu : u; }
+static inline int __float_as_int(float f) { int u; memcpy(&u, &f, 4); return f != f ? 0x7fffffff : u; }
 static inline float __uint_as_float(unsigned u) { float f; memcpy(&f, &u, 4); return f; }
 static inline float __int_as_float(int u) { float f; memcpy(&f, &u, 4); return f; }
 static inline int __viaddmin_s32_relu(int a, int b, int c) {

@@ -81,6 +81,17 @@ static int csort_threads(const float* data, long long pitch, long long N, int R,
     return 0;
 }
 
+// library entry (tests/test_k2_csort_emul.py): same arguments as csort_threads
+extern "C" int k2_csort_emulate_threads(const float* data, long long pitch, long long N, int R, float nodata,
+                                        long long n0, long long nn, int nplanes, const unsigned char* kind,
+                                        const double* q, float* out, long long out_pitch, int grid,
+                                        int tma_mode) {
+    if (R <= 32 || R > 1024 || pitch < 32 || (pitch & 31)) return -1;
+    return csort_threads(data, pitch, N, R, nodata, n0, nn, nplanes, kind, q, out, out_pitch, grid, tma_mode,
+                         nullptr);
+}
+
+#ifndef CSORT_LIB
 static unsigned long long rng_state = 0x2545F4914F6CDD1Dull;
 static unsigned rnd() {
     rng_state ^= rng_state << 13; rng_state ^= rng_state >> 7; rng_state ^= rng_state << 17;
@@ -172,3 +183,4 @@ int main(int argc, char** argv) {
     printf("clean\n");
     return 0;
 }
+#endif  // CSORT_LIB

@@ -39,3 +39,105 @@ def test_counting_sort_kernel_with_one_thread_per_cuda_thread(sanitizer):
     r = subprocess.run(args, capture_output=True, text=True, timeout=1800, env=env)
     assert r.returncode == 0 and 'clean' in r.stdout, (r.stdout[-2000:], r.stderr[-3000:])
     assert 'ThreadSanitizer' not in r.stderr
+
+
+import ctypes as C
+
+import numpy as np
+
+from oracle import np_oracle as O
+
+ND = -999.9
+QS = [round(0.05 * k, 2) for k in range(1, 20)]
+
+
+def csort_on_cpu(st, grid=3, tma_mode=0, mode=True, percentiles=QS, p=0.95):
+    """The counting-sort kernel, run on the CPU, on an [R, N] stack: planes in the
+    order of gsb_build_planes (mean, median, skew, var, std, coefvar, percentile
+    pair, percentile list, mode)."""
+    lib = C.CDLL(build_emul.build_csort_lib())
+    st = np.ascontiguousarray(st, np.float32)
+    R, N = st.shape
+    pitch = (N + 31) // 32 * 32
+    buf = np.full((R, pitch), 1.0e30, np.float32)
+    buf[:, :N] = st
+    kind = [0, 1, 2, 3, 4, 5, 1, 1] + [1] * len(percentiles) + ([6] if mode else [])
+    q = [0, .5, 0, 0, 0, 0, (1 - p) / 2, 1 - (1 - p) / 2] + list(percentiles) + ([0] if mode else [])
+    kind = np.array(kind, np.uint8)
+    q = np.array(q, np.float64)
+    out = np.full((len(kind), N), -12345.0, np.float32)
+    rc = lib.k2_csort_emulate_threads(
+        C.c_void_p(buf.ctypes.data), C.c_longlong(pitch), C.c_longlong(N), C.c_int(R), C.c_float(ND),
+        C.c_longlong(0), C.c_longlong(N), C.c_int(len(kind)), C.c_void_p(kind.ctypes.data),
+        C.c_void_p(q.ctypes.data), C.c_void_p(out.ctypes.data), C.c_longlong(N), C.c_int(grid),
+        C.c_int(tma_mode))
+    assert rc == 0
+    return out
+
+
+def check_like_the_gpu_suite(st, mode=True, percentiles=QS, p=0.95):
+    """tests/test_gpu_parity.py::check_grid, with the kernel on the CPU."""
+    st = np.ascontiguousarray(st, np.float32)
+    out = csort_on_cpu(st, mode=mode, percentiles=percentiles, p=p)
+    flags = 127 | (O.FLAG_MODE if mode else 0)
+    ref = O.grid_stats(st, ND, flags, p, percentiles)
+
+    def bits(a, b):
+        a = np.asarray(a, np.float64).astype(np.float32)
+        b = np.asarray(b, np.float64).astype(np.float32)
+        assert ((a == b) | (np.isnan(a) & np.isnan(b))).all()
+
+    def close(a, b, rtol=1e-5, atol=0.0):
+        a, b = np.asarray(a, float), np.asarray(b, float)
+        assert np.array_equal(np.isnan(a), np.isnan(b))
+        np.testing.assert_allclose(a, b, rtol=rtol, atol=atol, equal_nan=True)
+    sigma = np.nanmax(ref['stdmap']) if np.isfinite(ref['stdmap']).any() else 1.0
+    close(out[0], ref['meanmap'])
+    bits(out[1], ref['medianmap'])
+    close(out[2], ref['skewmap'], rtol=1e-5, atol=1e-5)
+    close(out[3], ref['varmap'], atol=1e-5 * sigma ** 2 * 1e-3)
+    close(out[4], ref['stdmap'], atol=1e-6 * sigma)
+    close(out[5], ref['coefvarmap'], atol=1e-6)
+    bits(out[6], ref['percmap'][:, 0])
+    bits(out[7], ref['percmap'][:, 1])
+    for i in range(len(percentiles)):
+        bits(out[8 + i], ref['percentiles'][:, i])
+    if mode:
+        bits(out[8 + len(percentiles)], ref['modemap'])
+
+
+@pytest.mark.parametrize('R', [100, 200, 1000])
+def test_leading_realizations_missing_same_data_as_the_gpu_test(R):
+    """tests/test_gpu_parity.py::test_moments_with_leading_realizations_missing,
+    with the counting-sort kernel on the CPU against the oracle and the GPU
+    suite's gates."""
+    if not os.path.exists(os.path.join(os.environ.get('CUDA_HOME', '/usr/local/cuda'), 'include', 'cuda.h')):
+        pytest.skip('CUDA headers not installed')
+    rng = np.random.default_rng(41)
+    st = None
+    for r_ in (100, 200, 1000):                    # the same random stream as the GPU test
+        s_ = np.round(rng.normal(800.0, 20.0, size=(r_, 64)) * 16) / 16
+        s_[:40, 8:24] = ND
+        s_[:r_ // 3, 24:32] = ND
+        s_[:r_ - 5, 32:36] = ND
+        if r_ == R:
+            st = s_
+    check_like_the_gpu_suite(st)
+
+
+def test_benchmark_columns_against_the_oracle():
+    """The benchmark generator's columns (clamp atoms, lattice ties, nodata) and
+    the edge columns of the GPU suite, R = 1000: every plane of the full call."""
+    if not os.path.exists(os.path.join(os.environ.get('CUDA_HOME', '/usr/local/cuda'), 'include', 'cuda.h')):
+        pytest.skip('CUDA headers not installed')
+    from gsimcli_b200 import synth
+    R = 1000
+    st = synth.stack(1003, R, [12, 8, 1])
+    st[:, 3] = 812.5
+    st[:, 4] = np.float32(ND)
+    st[:, 5] = np.float32(ND)
+    st[R // 2, 5] = 640.25
+    st[:, 6] = np.float32(ND)
+    st[0, 6], st[R - 1, 6] = 7.5, 8.5
+    st[:, 8] = np.where(np.arange(R) % 2 == 0, 500.0, 600.0)
+    check_like_the_gpu_suite(st)
