@@ -657,6 +657,47 @@ def run_extras(args):
     except Exception as exc:                              # noqa: BLE001
         out['k2_staged_select'] = {'error': repr(exc)[:300]}
 
+    # the same comparison on shallower stacks of the same size in bytes (config 4 reduces
+    # 500 realizations): default kernel vs the staged-select kernel at 16 warps
+    try:
+        depths = {}
+        for r2, nz in ((500, 50), (200, 125)):
+            try:
+                dims2 = [DIMS1[0], DIMS1[1], nz]
+                nn2 = int(np.prod(dims2))
+                g2 = gr.GridFiles.from_synthetic(SEED, r2, dims2, FIRST, CELLS, ND, device=0)
+                s2 = g2._stack
+                alg2 = 4.0 * r2 * nn2 + 4.0 * snp * nn2
+                res = {}
+                maps = {}
+                for name, algo in (('default', 0), ('staged_select_nw16', 4)):
+                    s2.set_option('k2_algo', algo)
+                    s2.set_option('k2_nw', 16 if algo else 0)
+                    d2 = torch.full((snp, nn2), -7.0, dtype=torch.float32, device='cuda')
+                    ms = []
+                    for i in range(4):
+                        e0.record()
+                        s2.stats_grid_device(sflags, 0.95, None, ND, 0, nn2, d2.data_ptr(), nn2, None)
+                        e1.record()
+                        e1.synchronize()
+                        if i:
+                            ms.append(e0.elapsed_time(e1))
+                    ms = float(np.mean(ms))
+                    res[name] = {'kernel_ms': ms, 'frac': alg2 / (ms * 1e-3) / 1e9 / peak,
+                                 'flagged_tiles': s2.k2_flagged()}
+                    maps[name] = d2
+                a2, b2 = maps['default'], maps['staged_select_nw16']
+                same2 = (a2.view(torch.int32) == b2.view(torch.int32)) | (torch.isnan(a2) & torch.isnan(b2))
+                res['values_not_bit_identical'] = int((~same2).sum())
+                depths['R%d' % r2] = res
+                del maps, a2, b2, d2, same2
+                g2.dump()
+            except Exception as exc:                      # noqa: BLE001
+                depths['R%d' % r2] = {'error': repr(exc)[:300]}
+        out['k2_staged_select_other_depths'] = depths
+    except Exception as exc:                              # noqa: BLE001
+        out['k2_staged_select_other_depths'] = {'error': repr(exc)[:300]}
+
     try:
         nrec, rows = 16, 16
         nbytes = nn * C4_WIDTH
