@@ -141,3 +141,13 @@ def test_benchmark_columns_against_the_oracle():
     st[0, 6], st[R - 1, 6] = 7.5, 8.5
     st[:, 8] = np.where(np.arange(R) % 2 == 0, 500.0, 600.0)
     check_like_the_gpu_suite(st)
+
+
+def test_short_differential_fuzz_against_the_oracle():
+    """25 random stacks of tests/emul/fuzz_csort.py (its docstring has the recorded
+    20-minute run): order statistics and mode bit for bit, moments at the gates."""
+    if not os.path.exists(os.path.join(os.environ.get('CUDA_HOME', '/usr/local/cuda'), 'include', 'cuda.h')):
+        pytest.skip('CUDA headers not installed')
+    from emul import fuzz_csort
+    runs, fails = fuzz_csort.run(20261020, stacks=25)
+    assert (runs, fails) == (25, 0)
