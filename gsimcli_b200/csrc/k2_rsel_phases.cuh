@@ -174,6 +174,48 @@ RS_HD unsigned long long mode_key(uint32_t mult, float v) {
     return (static_cast<unsigned long long>(mult) << 32) | (0xffffffffu - okey(v));
 }
 
+// ------------------------------------------------------------------ networks
+// ---- in-bin selection without data-dependent loops (lane = column: a loop whose
+// trip count is the bin's population would make the warp pay the largest bin of
+// its 32 columns squared).  The bin's values, padded with +INF, go through a
+// fixed odd-even merge sorting network in registers; the wanted order statistic
+// is picked with a select tree.
+RS_HD void cswap(float& a, float& b) {
+    const float lo = fminf(a, b), hi = fmaxf(a, b);
+    a = lo;
+    b = hi;
+}
+
+template <int K>
+RS_HD void sort_net(float (&v)[K]) {
+    // Batcher's odd-even merge sort, K a power of two (19 exchanges for 8, 63 for 16)
+#pragma unroll
+    for (int p = 1; p < K; p <<= 1)
+#pragma unroll
+        for (int k = p; k >= 1; k >>= 1)
+#pragma unroll
+            for (int j = k % p; j + k < K; j += 2 * k)
+#pragma unroll
+                for (int i = 0; i < k; ++i)
+                    if (i + j + k < K && (i + j) / (2 * p) == (i + j + k) / (2 * p))
+                        cswap(v[i + j], v[i + j + k]);
+}
+
+template <int K>
+RS_HD float pick(const float (&v)[K], int o) {
+    // v[o] for 0 <= o < K by a binary select tree on the bits of o
+    float t[K];
+#pragma unroll
+    for (int i = 0; i < K; ++i) t[i] = v[i];
+#pragma unroll
+    for (int step = 1; step < K; step <<= 1) {
+        const bool bit = (o & step) != 0;
+#pragma unroll
+        for (int i = 0; i + step < K; i += 2 * step) t[i] = bit ? t[i + step] : t[i];
+    }
+    return t[0];
+}
+
 // ------------------------------------------------------------------ pivot
 // first valid value among the thread's own rows -> pivc[w][c]
 template <int NW, int IPT>
@@ -189,44 +231,53 @@ RS_HD void phase_pivot_write(const Thr<IPT>& t, const Smem& s, const Args& a, in
     s.pivc[w * COLS + c] = cand;
 }
 
-// Pivot of the column = the candidate (one element per warp; the first 8 valid
-// ones are looked at) nearest to the candidates' mean.  It must be an element
-// (it stands in for missing values in min / max) and close to the mean: the
-// float32 shifted sums lose |pivot - mean| / sigma digits in the third moment
-// (first-valid-element pivots gave 5e-5 skewness errors on gamma columns).
+// Pivot of the column = the lower MEDIAN of the candidates (one element per warp:
+// the first valid value of warps 0..7).  It must be an element (it stands in for
+// missing values in min / max) and close to the mean: the float32 shifted sums
+// lose |pivot - mean| / sigma digits in the third moment.  (First-valid-element
+// pivots gave 5e-5 skewness errors on gamma columns; the candidate nearest to the
+// candidates' MEAN, used until the CPU fuzz of round 2, was dragged 4-5 sigma out
+// by one or two tail values when only a few candidates exist -- every second
+// realization missing left four -- and cost 1e-4 in the skewness.)
 // Every thread of the column computes the same value from the same words.
-template <int NW, int IPT>
-RS_HD void phase_pivot_read(Thr<IPT>& t, const Smem& s, int c) {
-    float cand[8];
-    float sum = 0.f;
+// `get(w)` = candidate of warp w (NaN: none).  The first 8 valid candidates in warp
+// order take part: warps 0..7 as a rule, later warps only when some of those have
+// no valid value at all.
+template <int NW, class F>
+RS_HD float pivot_of_candidates(F get) {
+    float v[8];
     int cnt = 0;
 #pragma unroll
     for (int w = 0; w < 8; ++w) {
-        const float v = s.pivc[w * COLS + c];
-        cand[w] = v;
-        if (v == v) { sum += v; ++cnt; }
+        const float x = get(w);
+        const bool ok = x == x;
+        v[w] = ok ? x : pinf();
+        cnt += ok ? 1 : 0;
     }
-    float p = 0.f;
-    if (cnt > 0) {
-        const float m = sum / static_cast<float>(cnt);
-        float bestd = pinf();
+    if (cnt < 8) {                                  // rare: top up from the other warps
+        for (int w = 8; w < NW && cnt < 8; ++w) {
+            const float x = get(w);
+            if (x == x) {
+                bool placed = false;
 #pragma unroll
-        for (int w = 0; w < 8; ++w) {
-            const float d = fabsf(cand[w] - m);       // NaN for a missing candidate: never < bestd
-            if (d < bestd) { bestd = d; p = cand[w]; }
-        }
-        if (!(bestd < pinf())) {                      // |v - m| overflowed: any candidate will do
-#pragma unroll
-            for (int w = 7; w >= 0; --w)
-                if (cand[w] == cand[w]) p = cand[w];
-        }
-    } else {
-        for (int w = 8; w < NW; ++w) {
-            const float v = s.pivc[w * COLS + c];
-            if (v == v) { p = v; break; }
+                for (int i = 0; i < 8; ++i) {
+                    const bool take = !placed && !(v[i] < pinf());
+                    v[i] = take ? x : v[i];
+                    placed = placed || take;
+                }
+                ++cnt;
+            }
         }
     }
-    t.piv = p;
+    if (cnt == 0) return 0.f;
+    sort_net<8>(v);
+    return pick<8>(v, (cnt - 1) >> 1);
+}
+
+template <int NW, int IPT>
+RS_HD void phase_pivot_read(Thr<IPT>& t, const Smem& s, int c) {
+    const float* pc = s.pivc + c;
+    t.piv = pivot_of_candidates<NW>([pc](int w) { return pc[w * COLS]; });
 }
 
 // ------------------------------------------------------------------ phase A
@@ -449,47 +500,6 @@ RS_HD ColView make_view(const Thr<IPT>& t, const Smem& s, int c) {
         v.reg0 = 0;
     }
     return v;
-}
-
-// ---- in-bin selection without data-dependent loops (lane = column: a loop whose
-// trip count is the bin's population would make the warp pay the largest bin of
-// its 32 columns squared).  The bin's values, padded with +INF, go through a
-// fixed odd-even merge sorting network in registers; the wanted order statistic
-// is picked with a select tree.
-RS_HD void cswap(float& a, float& b) {
-    const float lo = fminf(a, b), hi = fmaxf(a, b);
-    a = lo;
-    b = hi;
-}
-
-template <int K>
-RS_HD void sort_net(float (&v)[K]) {
-    // Batcher's odd-even merge sort, K a power of two (19 exchanges for 8, 63 for 16)
-#pragma unroll
-    for (int p = 1; p < K; p <<= 1)
-#pragma unroll
-        for (int k = p; k >= 1; k >>= 1)
-#pragma unroll
-            for (int j = k % p; j + k < K; j += 2 * k)
-#pragma unroll
-                for (int i = 0; i < k; ++i)
-                    if (i + j + k < K && (i + j) / (2 * p) == (i + j + k) / (2 * p))
-                        cswap(v[i + j], v[i + j + k]);
-}
-
-template <int K>
-RS_HD float pick(const float (&v)[K], int o) {
-    // v[o] for 0 <= o < K by a binary select tree on the bits of o
-    float t[K];
-#pragma unroll
-    for (int i = 0; i < K; ++i) t[i] = v[i];
-#pragma unroll
-    for (int step = 1; step < K; step <<= 1) {
-        const bool bit = (o & step) != 0;
-#pragma unroll
-        for (int i = 0; i + step < K; i += 2 * step) t[i] = bit ? t[i + step] : t[i];
-    }
-    return t[0];
 }
 
 // o-th (and, when o + 1 < cnt, (o+1)-th) smallest of the cnt <= K values of a bin

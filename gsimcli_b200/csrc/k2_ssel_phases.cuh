@@ -137,8 +137,8 @@ RS_HD float first_valid_of_warp(const float* col, int k, float nodata) {
 }
 
 // ------------------------------------------------------------------ phase A
-// Pivot = the candidate (first valid value of warps 0..7) nearest to the
-// candidates' mean -- rsel::phase_pivot_read, read straight from the stage so
+// Pivot = the lower median of the candidates (first valid value of warps 0..7)
+// -- rsel::pivot_of_candidates, read straight from the stage so
 // that no exchange and no barrier is needed; every thread of the column
 // computes the same value.  Then the thread's rows go to registers and into the
 // shifted sums; the pivot is an element of the column, so it stands in for
@@ -147,37 +147,11 @@ template <int NW, int IPT>
 RS_HD void phase_a(Thr<IPT>& t, const Smem& s, const Args& a, int w, int c) {
     static_assert(IPT % 2 == 0, "IPT must be even");
     const float* col = s.stage + c;
-    float p = 0.f;
-    {
-        float cand[8];
-        float sum = 0.f;
-        int cnt = 0;
-#pragma unroll
-        for (int k = 0; k < 8; ++k) {
-            const float v = first_valid_of_warp<NW, IPT>(col, k, a.nodata);
-            cand[k] = v;
-            if (v == v) { sum += v; ++cnt; }
-        }
-        if (cnt > 0) {
-            const float m = sum / static_cast<float>(cnt);
-            float bestd = pinf();
-#pragma unroll
-            for (int k = 0; k < 8; ++k) {
-                const float d = fabsf(cand[k] - m);       // NaN for a missing candidate: never < bestd
-                if (d < bestd) { bestd = d; p = cand[k]; }
-            }
-            if (!(bestd < pinf())) {                      // |v - m| overflowed: any candidate will do
-#pragma unroll
-                for (int k = 7; k >= 0; --k)
-                    if (cand[k] == cand[k]) p = cand[k];
-            }
-        } else {
-            for (int k = 8; k < NW; ++k) {
-                const float v = first_valid_of_warp<NW, IPT>(col, k, a.nodata);
-                if (v == v) { p = v; break; }
-            }
-        }
-    }
+    // rsel::pivot_of_candidates (lower median of the first 8 valid per-warp
+    // candidates), the candidates read straight from the stage
+    const float nodata = a.nodata;
+    const float p = rsel::pivot_of_candidates<NW>(
+        [col, nodata](int k) { return first_valid_of_warp<NW, IPT>(col, k, nodata); });
     t.piv = p;
     const float piv = p;
     float mn = piv, mx = piv;
