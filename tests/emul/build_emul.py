@@ -105,3 +105,18 @@ def build_csort_lib(force=False):
                     '-Wno-attributes', '-DCSORT_LIB', '-I' + cuda_inc, '-shared', '-fPIC', '-o', lib, CSORT_SRC],
                    check=True)
     return lib
+
+
+K1P_SRC = os.path.join(HERE, 'k1_parse_emul.cpp')
+K1P_HDR = os.path.join(HERE, '..', '..', 'gsimcli_b200', 'csrc', 'k1_parse.cuh')
+K1P_LIB = os.path.join(HERE, 'libk1parse_emul.so')
+
+
+def build_k1_parse(force=False):
+    """K1's general parsers (csrc/k1_parse.cuh) for the host."""
+    if (not force and os.path.exists(K1P_LIB)
+            and os.path.getmtime(K1P_LIB) >= max(os.path.getmtime(K1P_SRC), os.path.getmtime(K1P_HDR))):
+        return K1P_LIB
+    subprocess.run(['g++', '-O2', '-std=c++17', '-ffp-contract=off', '-shared', '-fPIC', '-o', K1P_LIB, K1P_SRC],
+                   check=True)
+    return K1P_LIB
