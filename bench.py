@@ -738,7 +738,7 @@ def run_extras(args):
     print(json.dumps({'extras': out}))
 
 
-def extras_subprocess(timeout=300):
+def extras_subprocess(timeout=240):
     """Runs ``bench.py --leg extras`` in its own process (own CUDA context, hard
     time limit) and returns its JSON object; never raises."""
     import subprocess
