@@ -120,3 +120,22 @@ def build_k1_parse(force=False):
     subprocess.run(['g++', '-O2', '-std=c++17', '-ffp-contract=off', '-shared', '-fPIC', '-o', K1P_LIB, K1P_SRC],
                    check=True)
     return K1P_LIB
+
+
+RSELT_SRC = os.path.join(HERE, 'k2_rsel_threads.cpp')
+RSELT_DEPS = [RSELT_SRC, os.path.join(HERE, 'cuda_threads_shim.h'), SRC, HDR,
+              os.path.join(HERE, '..', '..', 'gsimcli_b200', 'csrc', 'k2_rsel_kernel.cuh'),
+              os.path.join(HERE, '..', '..', 'gsimcli_b200', 'csrc', 'gsb_common.cuh')]
+
+
+def build_rsel_threads(sanitizer=None, force=False):
+    """Stand-alone driver of the THREADED emulation of the register-tile kernel's
+    tile loop (csrc/k2_rsel_kernel.cuh): ``sanitizer`` = None or 'thread'."""
+    exe = os.path.join(HERE, 'k2_rsel_threads_' + (sanitizer or 'plain'))
+    if not force and os.path.exists(exe) and os.path.getmtime(exe) >= max(os.path.getmtime(f) for f in RSELT_DEPS):
+        return exe
+    cuda_inc = os.path.join(os.environ.get('CUDA_HOME', '/usr/local/cuda'), 'include')
+    flags = ['-fsanitize=' + sanitizer, '-Wno-tsan'] if sanitizer else []
+    subprocess.run(['g++', '-O1', '-g', '-std=c++17', '-pthread', '-ffp-contract=off', '-Wno-unknown-pragmas',
+                    '-Wno-attributes', '-I' + cuda_inc] + flags + ['-o', exe, RSELT_SRC], check=True)
+    return exe

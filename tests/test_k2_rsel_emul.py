@@ -125,3 +125,21 @@ def test_emulated_kernel_flags_what_it_cannot_finish(emul_lib):
     st[0, 70], st[1, 70] = -50.0, 50.0                  # tile 2: heavy near-ties in one bin
     fl = check(emul_lib, st, 32)
     assert sorted(fl.tolist()) == [0, 1, 2]
+
+
+@pytest.mark.parametrize('sanitizer', [None, 'thread'])
+def test_kernel_function_with_one_thread_per_cuda_thread(sanitizer):
+    """The kernel function itself (csrc/k2_rsel_kernel.cuh: tile loop, barriers,
+    register prefetch of the next tile, the sort buffer that aliases the partial
+    sums, flagged-tile list) compiled for the host and run with one OS thread per
+    CUDA thread (tests/emul/cuda_threads_shim.h): planes bit-identical to the
+    serial emulation, same flagged tiles, no data race under ThreadSanitizer."""
+    import os
+    import subprocess
+    if not os.path.exists(os.path.join(os.environ.get('CUDA_HOME', '/usr/local/cuda'), 'include', 'cuda.h')):
+        pytest.skip('CUDA headers not installed')
+    exe = build_emul.build_rsel_threads(sanitizer)
+    env = dict(os.environ, TSAN_OPTIONS='halt_on_error=0 exitcode=66')
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=1800, env=env)
+    assert r.returncode == 0 and 'clean' in r.stdout, (r.stdout[-2000:], r.stderr[-3000:])
+    assert 'ThreadSanitizer' not in r.stderr
