@@ -304,11 +304,30 @@ def grid_stats(stack, nodata, flags, p=0.95, percentiles=None):
             med = (_take(s, (nn - 1) // 2) + _take(s, nn // 2)) / 2
             out['medianmap'] = np.where(n == 0, np.nan, med)
         if flags & FLAG_SKEW:
-            m3 = (adj2 * adj).sum(axis=0)
+            # pd.Series(arr).skew() (grid.py:687) = pandas.core.nanops.nanskew on the
+            # column in its ORIGINAL order, missing values set to 0: the sums are
+            # NumPy's pairwise sums over the contiguous column (a row of the
+            # transposed stack reduces with the very same inner loop).  The order
+            # matters for one thing only: nanskew zeroes m2 / m3 below a tolerance of
+            # (eps max|x|)^2 n, which is what makes the skewness of a CONSTANT column
+            # exactly 0 -- a mean summed in another order misses the constant by a
+            # few ulps more and lands on the other side of that tolerance (found by
+            # fuzzing the oracle against the reference on float64 stacks; float32
+            # stacks sum exactly in float64 and never got there).
+            raw = np.asarray(stack)
+            miss = (raw == (np.float32(nodata) if raw.dtype == np.float32 else nodata)) | np.isnan(raw)
+            vals = np.ascontiguousarray(np.where(miss, 0.0, raw.astype(np.float64)).T)     # [N, R]
+            missT = np.ascontiguousarray(miss.T)
+            mean_p = vals.sum(axis=1) / n
+            adjp = vals - mean_p[:, None]
+            adjp[missT] = 0.0
+            adjp2 = adjp ** 2
+            m2p = adjp2.sum(axis=1)
+            m3p = (adjp2 * adjp).sum(axis=1)
             eps = np.finfo(np.float64).eps
-            max_abs = np.abs(z).max(axis=0, initial=0.0)
-            m2z = np.where(np.abs(m2) < ((eps * max_abs) ** 2) * n, 0.0, m2)
-            m3z = np.where(np.abs(m3) < ((eps * max_abs) ** 3) * n, 0.0, m3)
+            max_abs = np.abs(vals).max(axis=1, initial=0.0)
+            m2z = np.where(np.abs(m2p) < ((eps * max_abs) ** 2) * n, 0.0, m2p)
+            m3z = np.where(np.abs(m3p) < ((eps * max_abs) ** 3) * n, 0.0, m3p)
             res = (n * (n - 1.0) ** 0.5 / (n - 2.0)) * (m3z / m2z ** 1.5)
             res = np.where(m2z == 0, 0.0, res)
             res = np.where(n < 3, np.nan, res)
