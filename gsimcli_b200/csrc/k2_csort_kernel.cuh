@@ -330,17 +330,24 @@ k2_csort_kernel(CS_PARAM CUtensorMap tmap, CS_PARAM K2Args a) {
                 // shifted sums lose |pivot - mean| / sigma digits in the third
                 // moment: a pivot taken blindly (first / median of three elements)
                 // sat 4 sigma out on skewed columns and cost 5e-5 in the skewness.
-                // (taken from the first group of 32 realizations that holds a valid
-                // value at all: with the first 32 missing, the old pivot 0 sat
-                // mean / sigma standard deviations out and the skewness of such a
-                // column was off by 1e-4 -- found by the host emulation,
-                // tests/emul/k2_csort_threads.cpp)
+                // (taken from the first group of 32 realizations that holds at least 8
+                // values: with the first 32 missing, the old pivot 0 sat mean / sigma
+                // standard deviations out and the skewness of such a column was off
+                // by 1e-4 and more -- found by the host emulation and its fuzz,
+                // tests/emul/k2_csort_threads.cpp, fuzz_csort.py)
                 float xp = xs[0];
                 uint32_t okm = __ballot_sync(FULL, xp < INF);
-                if (okm == 0u) {
+                if (__popc(okm) < 8) {
+                    // rare: fewer than 8 of the first 32 realizations exist -> the
+                    // first later group of 32 that holds 8, else the fullest one (a
+                    // group with one or two values makes a tail value the pivot)
 #pragma unroll
                     for (int j = 1; j < IPT; ++j)
-                        if (okm == 0u) { xp = xs[j]; okm = __ballot_sync(FULL, xp < INF); }
+                        if (__popc(okm) < 8) {
+                            const float xj = xs[j];
+                            const uint32_t mj = __ballot_sync(FULL, xj < INF);
+                            if (__popc(mj) > __popc(okm)) { okm = mj; xp = xj; }
+                        }
                 }
                 const bool ok0 = xp < INF;
                 const bool have_piv = okm != 0u;
