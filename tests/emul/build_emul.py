@@ -139,3 +139,27 @@ def build_rsel_threads(sanitizer=None, force=False):
     subprocess.run(['g++', '-O1', '-g', '-std=c++17', '-pthread', '-ffp-contract=off', '-Wno-unknown-pragmas',
                     '-Wno-attributes', '-I' + cuda_inc] + flags + ['-o', exe, RSELT_SRC], check=True)
     return exe
+
+
+KC_SRC = os.path.join(HERE, 'k2_columns_threads.cpp')
+KC_DEPS = [KC_SRC, os.path.join(HERE, 'cuda_threads_shim.h'),
+           os.path.join(HERE, '..', '..', 'gsimcli_b200', 'csrc', 'k2_columns_kernel.cuh'),
+           os.path.join(HERE, '..', '..', 'gsimcli_b200', 'csrc', 'gsb_common.cuh')]
+
+
+def build_columns(kind='lib', force=False):
+    """K2c / K3 (csrc/k2_columns_kernel.cuh) on the threaded CUDA model: ``kind`` =
+    'lib' (shared library for the Python fuzz) or 'thread' (stand-alone
+    ThreadSanitizer binary)."""
+    out = os.path.join(HERE, 'libk2columns_threads.so' if kind == 'lib' else 'k2_columns_threads_thread')
+    if not force and os.path.exists(out) and os.path.getmtime(out) >= max(os.path.getmtime(f) for f in KC_DEPS):
+        return out
+    cuda_inc = os.path.join(os.environ.get('CUDA_HOME', '/usr/local/cuda'), 'include')
+    base = ['g++', '-std=c++17', '-pthread', '-ffp-contract=off', '-Wno-unknown-pragmas', '-Wno-attributes',
+            '-I' + cuda_inc]
+    if kind == 'lib':
+        cmd = base + ['-O2', '-shared', '-fPIC', '-o', out, KC_SRC]
+    else:
+        cmd = base + ['-O1', '-g', '-DKC_MAIN', '-fsanitize=thread', '-Wno-tsan', '-o', out, KC_SRC]
+    subprocess.run(cmd, check=True)
+    return out

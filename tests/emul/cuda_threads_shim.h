@@ -26,7 +26,7 @@
 #include <vector>
 
 struct ShimDim { unsigned x; };
-static thread_local ShimDim threadIdx, blockIdx, gridDim;
+static thread_local ShimDim threadIdx, blockIdx, gridDim, blockDim;
 
 struct ShimWarp {
     pthread_barrier_t bar;
@@ -59,15 +59,18 @@ static inline void __syncwarp(unsigned = 0xffffffffu) { pthread_barrier_wait(&g_
 
 template <class T>
 static inline T shim_exchange(T v, int src) {
-    static_assert(sizeof(T) == 4, "32-bit values only");
-    uint32_t b;
-    memcpy(&b, &v, 4);
-    g_warp->xch[g_lane] = b;
-    pthread_barrier_wait(&g_warp->bar);
-    const uint32_t r = g_warp->xch[src & 31];
-    pthread_barrier_wait(&g_warp->bar);
+    static_assert(sizeof(T) == 4 || sizeof(T) == 8, "32- or 64-bit values only");
+    uint32_t b[2] = {0u, 0u};
+    memcpy(b, &v, sizeof(T));
+    uint32_t r[2];
+    for (int h = 0; h < static_cast<int>(sizeof(T) / 4); ++h) {
+        g_warp->xch[g_lane] = b[h];
+        pthread_barrier_wait(&g_warp->bar);
+        r[h] = g_warp->xch[src & 31];
+        pthread_barrier_wait(&g_warp->bar);
+    }
     T out;
-    memcpy(&out, &r, 4);
+    memcpy(&out, r, sizeof(T));
     return out;
 }
 template <class T> static inline T __shfl_sync(unsigned m, T v, int src) { if (m != 0xffffffffu) abort(); return shim_exchange(v, src); }
@@ -130,6 +133,7 @@ static inline int __viaddmin_s32_relu(int a, int b, int c) {
     if (s < 0) s = 0;
     return static_cast<int>(s);
 }
+static inline double __longlong_as_double(long long v) { double d; memcpy(&d, &v, 8); return d; }
 static inline float __fdiv_rn(float a, float b) { return a / b; }
 static inline double __dmul_rn(double a, double b) { return a * b; }
 static inline double __dadd_rn(double a, double b) { return a + b; }
@@ -217,13 +221,14 @@ static void shim_run_block(int block, int grid, int nthreads, size_t smem_bytes,
     std::vector<std::thread> th;
     th.reserve(nthreads);
     for (int t = 0; t < nthreads; ++t)
-        th.emplace_back([&blk, block, grid, t, &kernel]() {
+        th.emplace_back([&blk, block, grid, t, nthreads, &kernel]() {
             g_blk = &blk;
             g_warp = blk.warps + (t >> 5);
             g_lane = t & 31;
             threadIdx.x = static_cast<unsigned>(t);
             blockIdx.x = static_cast<unsigned>(block);
             gridDim.x = static_cast<unsigned>(grid);
+            blockDim.x = static_cast<unsigned>(nthreads);
             kernel();
         });
     for (auto& t : th) t.join();
