@@ -345,8 +345,8 @@ def grid_stats(stack, nodata, flags, p=0.95, percentiles=None):
                 [_quantile_cols(s, n, (1 - p) / 2),
                  _quantile_cols(s, n, 1 - (1 - p) / 2)], axis=1)
         if percentiles is not None:
-            out['percentiles'] = np.stack(
-                [_quantile_cols(s, n, q) for q in percentiles], axis=1)
+            out['percentiles'] = (np.stack([_quantile_cols(s, n, q) for q in percentiles], axis=1)
+                                  if len(percentiles) else np.empty((N, 0)))
         if flags & FLAG_MODE:
             idx = np.arange(R)[:, None]
             newrun = np.ones((R, N), dtype=bool)
