@@ -10,8 +10,9 @@ zero-inflated, values centred on zero over 13 decades, constants, heavy tails)
 with six missing-value patterns (leading, trailing, random, every second, all).
 Gates: medians, percentile pair, 19 percentiles and the mode bit for bit; variance,
 std and skewness at the GPU suite's tolerances; the mean to 1e-5 relative OR 2e-7
-sigma (a float32 sum cannot do better on a mean that is ~0 against its sigma: the
-one class of deviations the fuzzing found, at most 1.5e-7 sigma).
+sigma (a float32 quotient cannot do better on a mean that is ~0 against its sigma:
+the one class of deviations the fuzzing found, 1.5e-7 sigma with the first pivot
+rule, below 5e-8 sigma since).
 Recorded runs (round 2): seed 7, 20 minutes, 4 251 stacks (~2*10^5 columns): no
 order-statistic, mode, variance or skewness deviation; seed 99, 30 minutes, 6 876
 stacks: one skewness 1.8e-5 off (a column whose first 127 realizations are
