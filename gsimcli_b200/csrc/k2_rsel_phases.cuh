@@ -564,20 +564,29 @@ RS_HD bool rank_pair(const ColView& v, int r, bool want1, bool wide, float* g0, 
     const bool atom0 = locate(v, r, g0, &start, &cnt, &o);
     bool same_bin = false;
     if (!atom0) {
-        if (cnt > RS_BIGBIN) return false;
         const float* p = v.buf + start * COLS;
         float h1 = 0.f;
-        if (cnt > 16) select_loop(p, cnt, o, g0, &h1);
+        if (cnt > RS_BIGBIN) {
+            // too many values to select from -- unless they are all equal (heavy
+            // ties: quantised data put hundreds of equal values into one bin),
+            // in which case every rank of the bin is that value
+            float mn = p[0], mx = p[0];
+            for (int i = 1; i < cnt; ++i) {
+                const float x = p[i * COLS];
+                mn = fminf(mn, x);
+                mx = fmaxf(mx, x);
+            }
+            if (mn != mx) return false;
+            *g0 = mn;
+            h1 = mn;
+        } else if (cnt > 16) select_loop(p, cnt, o, g0, &h1);
         else if (wide || cnt > 8) select_net<16>(p, cnt, o, g0, &h1);
         else select_net<8>(p, cnt, o, g0, &h1);
         if (o + 1 < cnt) { *g1 = h1; same_bin = true; }
     }
     if (!want1 || same_bin) return true;
     const bool atom1 = locate(v, r + 1, g1, &start, &cnt, &o);
-    if (!atom1) {
-        if (cnt > RS_BIGBIN) return false;
-        *g1 = bin_min(v.buf + start * COLS, cnt);     // o == 0: first value of its bin
-    }
+    if (!atom1) *g1 = bin_min(v.buf + start * COLS, cnt);     // o == 0: first value of its bin (any size)
     return true;
 }
 
