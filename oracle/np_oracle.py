@@ -290,13 +290,24 @@ def grid_stats(stack, nodata, flags, p=0.95, percentiles=None):
     s, n = _sorted_valid(np.asarray(stack), nodata)
     R, N = s.shape
     out = {}
-    valid = ~np.isnan(s)
-    z = np.where(valid, s, 0.0)
+    # The moments are summed the way the library calls of the reference sum them
+    # (np.nanmean / np.nanvar standing in for bottleneck, pandas' nanskew): over the
+    # column in its ORIGINAL order, missing values set to 0, with NumPy's pairwise
+    # summation -- a row of the transposed stack reduces with the very same inner
+    # loop as the 1-D column.  At 1e-16 the order is visible only where the
+    # reference's result is itself decided by rounding: the coefficient of
+    # variation of a column whose mean cancels to ~0, and pandas' zeroing of the
+    # second / third moment of a CONSTANT column (below).
+    raw = np.asarray(stack)
+    miss = (raw == (np.float32(nodata) if raw.dtype == np.float32 else nodata)) | np.isnan(raw)
+    vals = np.ascontiguousarray(np.where(miss, 0.0, raw.astype(np.float64)).T)     # [N, R]
+    missT = np.ascontiguousarray(miss.T)
     with np.errstate(all='ignore'):
-        mean = z.sum(axis=0) / n
-        adj = np.where(valid, s - mean[None, :], 0.0)
-        adj2 = adj * adj
-        m2 = adj2.sum(axis=0)
+        mean = vals.sum(axis=1) / n
+        adjp = vals - mean[:, None]
+        adjp[missT] = 0.0
+        adjp2 = adjp ** 2
+        m2 = adjp2.sum(axis=1)
         if flags & FLAG_MEAN:
             out['meanmap'] = mean
         if flags & FLAG_MED:
@@ -314,15 +325,7 @@ def grid_stats(stack, nodata, flags, p=0.95, percentiles=None):
             # few ulps more and lands on the other side of that tolerance (found by
             # fuzzing the oracle against the reference on float64 stacks; float32
             # stacks sum exactly in float64 and never got there).
-            raw = np.asarray(stack)
-            miss = (raw == (np.float32(nodata) if raw.dtype == np.float32 else nodata)) | np.isnan(raw)
-            vals = np.ascontiguousarray(np.where(miss, 0.0, raw.astype(np.float64)).T)     # [N, R]
-            missT = np.ascontiguousarray(miss.T)
-            mean_p = vals.sum(axis=1) / n
-            adjp = vals - mean_p[:, None]
-            adjp[missT] = 0.0
-            adjp2 = adjp ** 2
-            m2p = adjp2.sum(axis=1)
+            m2p = m2
             m3p = (adjp2 * adjp).sum(axis=1)
             eps = np.finfo(np.float64).eps
             max_abs = np.abs(vals).max(axis=1, initial=0.0)
@@ -352,7 +355,7 @@ def grid_stats(stack, nodata, flags, p=0.95, percentiles=None):
             newrun = np.ones((R, N), dtype=bool)
             newrun[1:] = s[1:] != s[:-1]
             start = np.maximum.accumulate(np.where(newrun, idx, 0), axis=0)
-            runlen = np.where(valid, idx - start + 1, 0)
+            runlen = np.where(~np.isnan(s), idx - start + 1, 0)
             pos = runlen.argmax(axis=0)          # first longest run's end
             mode = _take(s, pos)
             out['modemap'] = np.where(n == 0, np.nan, mode)
