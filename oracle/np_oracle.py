@@ -299,9 +299,10 @@ def grid_stats(stack, nodata, flags, p=0.95, percentiles=None):
     # variation of a column whose mean cancels to ~0, and pandas' zeroing of the
     # second / third moment of a CONSTANT column (below).
     raw = np.asarray(stack)
-    miss = (raw == (np.float32(nodata) if raw.dtype == np.float32 else nodata)) | np.isnan(raw)
-    vals = np.ascontiguousarray(np.where(miss, 0.0, raw.astype(np.float64)).T)     # [N, R]
-    missT = np.ascontiguousarray(miss.T)
+    nd64 = np.float64(np.float32(nodata)) if raw.dtype == np.float32 else np.float64(nodata)
+    vals = np.array(raw.T, dtype=np.float64, order='C')                             # [N, R]
+    missT = (vals == nd64) | np.isnan(vals)
+    vals[missT] = 0.0
     with np.errstate(all='ignore'):
         mean = vals.sum(axis=1) / n
         adjp = vals - mean[:, None]
